@@ -1,0 +1,28 @@
+"""B200-native (sm_100a) implementation of the 3D acoustic FDTD hot path of
+ycnliu/Accelerated-3D-Acoustic-FDTD-Kernel behind the reference's own operator ABI.
+
+The product is ``libfdtd_b200.so`` (csrc/, C ABI in include/fdtd_b200.h).  This package is the
+thin Python host mirror used by the tests and bench: same names and argument meaning as the
+reference's ``Kernel_*`` entry points.  There is no CPU fallback: importing works without a GPU,
+but every compute call goes to the CUDA library and raises if it cannot run.
+"""
+from .host import (  # noqa: F401
+    HALO,
+    WARMUP_STEPS,
+    Dataobj,
+    FdtdError,
+    Geometry,
+    Plan,
+    Profiler,
+    FDTD_SetRuntimeConfig,
+    Kernel_B200,
+    Kernel_CUDA_Optimized,
+    build,
+    exported_symbols,
+    fill_ricker,
+    fill_source_coords,
+    lib,
+    lib_path,
+    source_table,
+    write_benchmark_csv,
+)

@@ -1,0 +1,151 @@
+// fdtd_abi.cu -- the reference's operator boundary (Kernel_*), rebuilt on resident plans, plus the
+// host-only helpers of include/fdtd_b200.h (driver input synthesis, benchmark.csv row writer).
+#include "fdtd_plan.h"
+
+#include <math.h>
+#include <string.h>
+
+#include <fstream>
+
+using namespace fdtd;
+
+// ---------------------------------------------------------------------------- Kernel_* (reference ABI)
+// Replaces Kernel_CUDA_Optimized (cuda_optimized.cu:282-514).  Per call: create plan (device
+// alloc), H2D of u (3 levels) and m, source table, 5 untimed + timed steps, D2H of u, free --
+// the same life cycle as cuda.cu:204-214,317-320, so no state survives the call.
+static int kernel_entry(struct dataobj *m_vec, struct dataobj *src_vec, struct dataobj *src_coords_vec,
+                        struct dataobj *u_vec, int x_M, int x_m, int y_M, int y_m, int z_M, int z_m, float dt,
+                        float h_x, float h_y, float h_z, float o_x, float o_y, float o_z, int p_src_M, int p_src_m,
+                        int time_M, int time_m, int deviceid, int devicerm, struct profiler *timers)
+{
+    (void)devicerm;  // device memory never outlives the call (cuda.cu:321 ignores it too)
+    if (timers) timers->section0 = timers->section1 = 0.0;  // overwrite, like cuda_optimized.cu:290
+    if (!m_vec || !u_vec || !u_vec->data || !m_vec->data || !u_vec->size || !m_vec->size)
+        return (int)cudaErrorInvalidValue;
+    if (u_vec->size[0] != 3) return (int)cudaErrorInvalidValue;
+
+    PlanShape s{};
+    s.nxp = u_vec->size[1];
+    s.nyp = u_vec->size[2];
+    s.nzp = u_vec->size[3];
+    if (m_vec->size[0] != s.nxp || m_vec->size[1] != s.nyp || m_vec->size[2] != s.nzp)
+        return (int)cudaErrorInvalidValue;
+    s.x_m = x_m; s.x_M = x_M; s.y_m = y_m; s.y_M = y_M; s.z_m = z_m; s.z_M = z_M;
+    s.dt = dt; s.h_x = h_x; s.h_y = h_y; s.h_z = h_z; s.o_x = o_x; s.o_y = o_y; s.o_z = o_z;
+    s.x_offset = 0;
+    s.gx_m = x_m;
+    s.gx_M = x_M;
+    s.deviceid = deviceid;
+
+    fdtd_b200_plan *p = nullptr;
+    int rc = plan_create_internal(s, &p);
+    if (rc) return rc;
+    rc = fdtd_b200_plan_upload(p, (const float *)u_vec->data, (const float *)m_vec->data);
+    // "no sources" is p_src_M < p_src_m, an empty src array, or null data (main.cpp:537-545,556)
+    const bool has_src = src_vec && src_coords_vec && src_vec->size && src_coords_vec->size && src_vec->data &&
+                         src_coords_vec->data && src_vec->size[0] * src_vec->size[1] > 0 && p_src_M - p_src_m + 1 > 0;
+    if (!rc && has_src)
+        rc = fdtd_b200_plan_set_sources(p, (const float *)src_vec->data, src_vec->size[0], src_vec->size[1],
+                                        (const float *)src_coords_vec->data, src_coords_vec->size[0],
+                                        src_coords_vec->size[1], p_src_m, p_src_M);
+    if (!rc) rc = fdtd_b200_plan_run(p, time_m, time_M, timers);
+    if (!rc) rc = fdtd_b200_plan_download(p, (float *)u_vec->data);
+    fdtd_b200_plan_destroy(p);
+    return rc;
+}
+
+extern "C" int Kernel_B200(struct dataobj *__restrict m_vec, struct dataobj *__restrict src_vec,
+                           struct dataobj *__restrict src_coords_vec, struct dataobj *__restrict u_vec, const int x_M,
+                           const int x_m, const int y_M, const int y_m, const int z_M, const int z_m, const float dt,
+                           const float h_x, const float h_y, const float h_z, const float o_x, const float o_y,
+                           const float o_z, const int p_src_M, const int p_src_m, const int time_M, const int time_m,
+                           const int deviceid, const int devicerm, struct profiler *timers)
+{
+    return kernel_entry(m_vec, src_vec, src_coords_vec, u_vec, x_M, x_m, y_M, y_m, z_M, z_m, dt, h_x, h_y, h_z, o_x,
+                        o_y, o_z, p_src_M, p_src_m, time_M, time_m, deviceid, devicerm, timers);
+}
+
+extern "C" int Kernel_CUDA_Optimized(struct dataobj *__restrict m_vec, struct dataobj *__restrict src_vec,
+                                     struct dataobj *__restrict src_coords_vec, struct dataobj *__restrict u_vec,
+                                     const int x_M, const int x_m, const int y_M, const int y_m, const int z_M,
+                                     const int z_m, const float dt, const float h_x, const float h_y, const float h_z,
+                                     const float o_x, const float o_y, const float o_z, const int p_src_M,
+                                     const int p_src_m, const int time_M, const int time_m, const int deviceid,
+                                     const int devicerm, struct profiler *timers)
+{
+    return kernel_entry(m_vec, src_vec, src_coords_vec, u_vec, x_M, x_m, y_M, y_m, z_M, z_m, dt, h_x, h_y, h_z, o_x,
+                        o_y, o_z, p_src_M, p_src_m, time_M, time_m, deviceid, devicerm, timers);
+}
+
+// ---------------------------------------------------------------------------- x-slab neighbours
+// (implemented in fdtd_slab.cu)
+
+// ---------------------------------------------------------------------------- host-only helpers
+// Ricker wavelet of the driver, main.cpp:290-298 (f0 = 10, all fp32).
+extern "C" void fdtd_b200_fill_ricker(float *src, int T, int S, float dt)
+{
+    const float f0 = 10.0f;
+    for (int t = 0; t < T; ++t) {
+        const float tshift = t * dt - 1.0f / f0;
+        const float a = float(M_PI) * float(M_PI) * f0 * f0 * tshift * tshift;
+        const float val = (1.0f - 2.0f * a) * expf(-a);
+        for (int s = 0; s < S; ++s) src[(size_t)t * S + s] = val;
+    }
+}
+
+// Source lattice of the driver, main.cpp:301-325: sources 0..26 on {0.25,0.5,0.75}*(n-1)*0.1f
+// (x outermost, z innermost), every further source at the grid centre 0.5f*(n-1)*h.
+extern "C" void fdtd_b200_fill_source_coords(float *coords, int S, int nx, int ny, int nz, float h_x, float h_y,
+                                             float h_z)
+{
+    const float f[3] = {0.25f, 0.50f, 0.75f};
+    const float h = 0.1f;  // main.cpp:304 uses the literal, not h_x
+    const float L[3] = {(nx - 1) * h, (ny - 1) * h, (nz - 1) * h};
+    int placed = 0;
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j)
+            for (int k = 0; k < 3 && placed < S; ++k, ++placed) {
+                coords[3 * placed + 0] = f[i] * L[0];
+                coords[3 * placed + 1] = f[j] * L[1];
+                coords[3 * placed + 2] = f[k] * L[2];
+            }
+    for (; placed < S; ++placed) {
+        coords[3 * placed + 0] = 0.5f * (nx - 1) * h_x;
+        coords[3 * placed + 1] = 0.5f * (ny - 1) * h_y;
+        coords[3 * placed + 2] = 0.5f * (nz - 1) * h_z;
+    }
+}
+
+// One row of benchmark.csv in the reference's schema (main.cpp:222-248): header written when the
+// file does not exist yet, efficiencies against the peaks the caller detected.
+extern "C" int fdtd_b200_write_benchmark_csv(const char *filename, const char *method, double total_s,
+                                             double total_std, double s0_s, double s0_std, double s1_s, double s1_std,
+                                             double device_s, double device_std, double overhead_s,
+                                             double overhead_std, double gflops, double gflops_std, double gbps,
+                                             double gbps_std, double peak_fp32_gf, double peak_bw_gbs, double ai,
+                                             int nx, int ny, int nz, int timesteps, int nsrc, int stencil_order)
+{
+    if (!filename || !method) return (int)cudaErrorInvalidValue;
+    bool exists;
+    {
+        std::ifstream test(filename);
+        exists = test.good();
+    }
+    std::ofstream file(filename, std::ios::app);
+    if (!file) return (int)cudaErrorInvalidValue;
+    if (!exists)
+        file << "Method,Total_Time(ms),Total_Std(ms),Section0_Time(ms),Section0_Std(ms),"
+                "Section1_Time(ms),Section1_Std(ms),Device_Time(ms),Device_Std(ms),"
+                "Overhead(ms),Overhead_Std(ms),GFLOPS,GFLOPS_Std,GBps,GBps_Std,Compute_Eff(%),Memory_Eff(%),"
+                "AI,NX,NY,NZ,Timesteps,Sources,StencilOrder\n";
+    const double ceff = peak_fp32_gf > 0.0 ? gflops / peak_fp32_gf * 100.0 : 0.0;
+    const double meff = peak_bw_gbs > 0.0 ? gbps / peak_bw_gbs * 100.0 : 0.0;
+    file << method << "," << total_s * 1000 << "," << total_std * 1000 << "," << s0_s * 1000 << "," << s0_std * 1000
+         << "," << s1_s * 1000 << "," << s1_std * 1000 << "," << device_s * 1000 << "," << device_std * 1000 << ","
+         << overhead_s * 1000 << "," << overhead_std * 1000 << "," << gflops << "," << gflops_std << "," << gbps << ","
+         << gbps_std << "," << ceff << "," << meff << "," << ai << "," << nx << "," << ny << "," << nz << ","
+         << timesteps << "," << nsrc << "," << stencil_order << "\n";
+    return file.good() ? 0 : (int)cudaErrorInvalidValue;
+}
+
+extern "C" const char *fdtd_b200_version(void) { return "fdtd_b200 0.1 (sm_100a)"; }

@@ -1,0 +1,54 @@
+// fdtd_common.cuh -- shared types of the B200 FDTD hot path (device + host).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define FDTD_HALO 4          // reference main.cpp:27-32: HALO == STENCIL_ORDER == 4 cells
+#define FDTD_WARMUP_STEPS 5  // reference openacc.cpp:5
+
+#define FDTD_CHECK(expr)                         \
+    do {                                         \
+        cudaError_t _e = (expr);                 \
+        if (_e != cudaSuccess) return (int)_e;   \
+    } while (0)
+
+namespace fdtd {
+
+// Scalar coefficients of one step, all fp32, computed on the host exactly as openacc.cpp:84-87.
+struct Coef {
+    float dt2;   // dt*dt
+    float r1;    // 1/(dt*dt)
+    float n2r1;  // -2.0f*r1
+    float r2, r3, r4;  // 1/h_x^2, 1/h_y^2, 1/h_z^2
+};
+
+// One grid cell that receives source contributions (padded local coordinates).
+struct SourceCell {
+    int X, Y, Z;
+    int first, count;  // range in the contribution list, ascending p_src (the serial oracle's order)
+};
+struct SourceContrib {
+    int p;     // source index (column of src[time][p], row of mbase)
+    float w;   // ((1e-2f*wx)*wy)*wz  -- openacc.cpp:134, time independent
+};
+
+// Device view of the per-step scatter work.
+struct SourceView {
+    const int *plane_off;          // [nxp+1] offsets into cells[] by padded X, interior cells only
+    const SourceCell *cells;       // interior cells sorted by (X,Y,Z)
+    const SourceContrib *contribs;
+    const float *src_row;          // src + time*pstride
+    const float *mbase;            // m at each source's base corner, indexed by p
+    int ncells;
+};
+
+// Field geometry of one slab as the kernels see it.
+struct Grid {
+    int nxp, nyp, nzp;       // padded extents
+    int X0, X1;              // padded x range [X0, X1) updated by this launch
+    int Y0, Y1, Z0, Z1;      // padded y / z interior ranges [.., ..)
+    long long lvl;           // elements per level
+};
+
+}  // namespace fdtd

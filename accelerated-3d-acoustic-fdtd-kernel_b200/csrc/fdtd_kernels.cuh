@@ -1,0 +1,51 @@
+// fdtd_kernels.cuh -- launch interface of the device kernels (implemented in stencil_*.cu, inject.cu).
+#pragma once
+#include "fdtd_common.cuh"
+
+namespace fdtd {
+
+// Everything one Section0 launch needs besides the kernel-variant specifics.
+struct StepArgs {
+    float *u;          // base of u[3][nxp][nyp][nzp]
+    const float *m;    // m[nxp][nyp][nzp]
+    Grid g;
+    Coef k;
+    int t0, t1, t2;    // ring: current, previous, next
+    SourceView sv;     // sv.ncells == 0 -> no fused injection
+};
+
+// --- generic kernel: any extents / alignment, one point per thread, loads through L1/L2.
+int launch_stencil_generic(const StepArgs &a, bool exact, cudaStream_t stream);
+
+// --- 2.5D x-streaming kernel: TMA -> mbarrier ring in shared memory -> register queue along x.
+struct TmaConfig {
+    int ty = 0, tz = 0;  // (y,z) tile; 0 = auto
+    int stages = 0;      // halo-plane ring depth S0 (centre ring has S0-2 slots)
+    int xchunk = 0;      // x planes per CTA; 0 = auto
+};
+struct TmaPlan {         // built once per (arrays, config): tensor maps + launch shape
+    alignas(64) CUtensorMap map_halo;  // u as (z,y,x,t), box (tz+8, ty+4, 1, 1)
+    alignas(64) CUtensorMap map_ctr;   // u as (z,y,x,t), box (tz, ty, 1, 1)
+    alignas(64) CUtensorMap map_m;     // m as (z,y,x),   box (tz, ty, 1)
+    int ty, tz, stages, xchunk;
+    int variant;         // index into the instantiation table
+    size_t smem_bytes;
+    bool valid = false;
+};
+// Can the TMA kernel run on this geometry?  (row pitch and z origin 16-byte aligned, nz % 4 == 0)
+bool tma_supported(const Grid &g);
+int tma_plan_build(TmaPlan &p, float *u, const float *m, const Grid &g, const TmaConfig &cfg, bool exact,
+                   int sm_count);
+int launch_stencil_tma(const TmaPlan &p, const StepArgs &a, bool exact, cudaStream_t stream);
+
+// --- Section1 stand-alone scatter: one thread per cell, contributions added in p_src order.
+int launch_scatter(float *u_level, const Grid &g, const SourceCell *cells, int ncells,
+                   const SourceContrib *contribs, const float *src_row, const float *mbase,
+                   cudaStream_t stream);
+// mbase[i] = m[base_idx[i]] (base corner of every source), i < n.
+int launch_gather_mbase(const float *m, const long long *base_idx, float *mbase, int n, cudaStream_t stream);
+// Fills.
+int launch_fill(float *p, size_t n, float v, cudaStream_t stream);
+int launch_fill_dense(float *u, float *m, int nxp, int nyp, int nzp, long long x_plane_offset, cudaStream_t stream);
+
+}  // namespace fdtd

@@ -1,0 +1,474 @@
+// fdtd_plan.cu -- host side of libfdtd_b200.so: resident plans, the time loop with the 3-level
+// ring, the source table, and the reference's operator ABI on top of them.
+//
+// Mirrors the reference's host wrappers (openacc.cpp:61-216, cuda.cu:173-323,
+// cuda_optimized.cu:282-514): per call alloc -> H2D -> 5 untimed steps -> timed steps -> D2H -> free,
+// timers for the steps time >= time_m + 5 only.  What is different by design: every CUDA call is
+// checked and its cudaError_t returned, section timers are measured with CUDA events on the
+// compute stream (no fake 85/15 split, cuda_optimized.cu:469-470), no redundant shadow copies of u.
+#include "fdtd_plan.h"
+
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <fstream>
+#include <map>
+#include <tuple>
+#include <vector>
+
+using namespace fdtd;
+
+// ---------------------------------------------------------------------------- runtime config
+static int g_use_tc = 0, g_t_fuse = 1, g_nfields = 1;
+
+extern "C" void FDTD_SetRuntimeConfig(int use_tc, int t_fuse, int nfields)
+{
+    g_use_tc = use_tc;                       // accepted, ignored: the stencil is not a contraction
+    g_t_fuse = t_fuse < 1 ? 1 : t_fuse;      // temporal-blocking depth requested by the driver
+    g_nfields = nfields < 1 ? 1 : nfields;   // only 1 field is supported; larger values are ignored
+}
+
+static int env_int(const char *key, int fallback)
+{
+    const char *v = getenv(key);
+    return (v && *v) ? atoi(v) : fallback;
+}
+
+// ---------------------------------------------------------------------------- source table (host, IEEE fp32)
+// One axis of openacc.cpp:125-131: g = (-o + c)/h ; pos = (int)floor(g) ; frac = -floor(g) + g.
+static inline void source_axis(float coord, float o, float h, int *pos, float *frac)
+{
+    const float gq = (-o + coord) / h;
+    const float fl = floorf(gq);
+    *pos = (int)fl;
+    *frac = -fl + gq;
+}
+// Trilinear weight of one axis, openacc.cpp:134: r*p + (1 - r)*(1 - p), r in {0,1} as float.
+static inline float axis_weight(int r, float p) { return (float)r * p + (float)(1 - r) * (1.0f - p); }
+
+extern "C" int fdtd_b200_source_table(const float coord[3], const float o[3], const float h[3], const int lo[3],
+                                      const int hi[3], int pos[3], float frac[3], float w[8], int in_range[8])
+{
+    for (int a = 0; a < 3; ++a) source_axis(coord[a], o[a], h[a], &pos[a], &frac[a]);
+    for (int rx = 0; rx <= 1; ++rx)
+        for (int ry = 0; ry <= 1; ++ry)
+            for (int rz = 0; rz <= 1; ++rz) {
+                const int i = rx * 4 + ry * 2 + rz;
+                w[i] = 1.0e-2F * axis_weight(rx, frac[0]) * axis_weight(ry, frac[1]) * axis_weight(rz, frac[2]);
+                in_range[i] = rx + pos[0] >= lo[0] - 1 && ry + pos[1] >= lo[1] - 1 && rz + pos[2] >= lo[2] - 1 &&
+                              rx + pos[0] <= hi[0] + 1 && ry + pos[1] <= hi[1] + 1 && rz + pos[2] <= hi[2] + 1;
+            }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------- plan life cycle
+static void plan_free_sources(fdtd_b200_plan *p)
+{
+    cudaFree(p->d_src);
+    cudaFree(p->d_cells);
+    cudaFree(p->d_contribs);
+    cudaFree(p->d_plane_off);
+    cudaFree(p->d_mbase);
+    cudaFree(p->d_base_idx);
+    p->d_src = nullptr;
+    p->d_cells = nullptr;
+    p->d_contribs = nullptr;
+    p->d_plane_off = nullptr;
+    p->d_mbase = nullptr;
+    p->d_base_idx = nullptr;
+    p->ncells_int = p->ncells_halo = p->ncells_all = 0;
+    p->n_mbase = 0;
+    p->src_size0 = 0;
+}
+
+int fdtd::plan_create_internal(const PlanShape &s, fdtd_b200_plan **out)
+{
+    if (!out) return (int)cudaErrorInvalidValue;
+    *out = nullptr;
+    // extents must be non-empty (cuda_optimized.cu:347) and leave the radius-2 star inside the arrays
+    if (s.x_M < s.x_m || s.y_M < s.y_m || s.z_M < s.z_m) return (int)cudaErrorInvalidValue;
+    if (s.x_m + FDTD_HALO - 2 < 0 || s.y_m + FDTD_HALO - 2 < 0 || s.z_m + FDTD_HALO - 2 < 0 ||
+        s.x_M + FDTD_HALO + 2 >= s.nxp || s.y_M + FDTD_HALO + 2 >= s.nyp || s.z_M + FDTD_HALO + 2 >= s.nzp)
+        return (int)cudaErrorInvalidValue;
+    if (s.deviceid != -1) FDTD_CHECK(cudaSetDevice(s.deviceid));
+
+    fdtd_b200_plan *p = new fdtd_b200_plan();
+    p->shape = s;
+    FDTD_CHECK(cudaGetDevice(&p->dev));
+    cudaDeviceGetAttribute(&p->sm_count, cudaDevAttrMultiProcessorCount, p->dev);
+    p->g.nxp = s.nxp;
+    p->g.nyp = s.nyp;
+    p->g.nzp = s.nzp;
+    p->g.X0 = s.x_m + FDTD_HALO;
+    p->g.X1 = s.x_M + FDTD_HALO + 1;
+    p->g.Y0 = s.y_m + FDTD_HALO;
+    p->g.Y1 = s.y_M + FDTD_HALO + 1;
+    p->g.Z0 = s.z_m + FDTD_HALO;
+    p->g.Z1 = s.z_M + FDTD_HALO + 1;
+    p->g.lvl = (long long)s.nxp * s.nyp * s.nzp;
+    // openacc.cpp:84-87, fp32 on the host
+    p->k.dt2 = s.dt * s.dt;
+    p->k.r1 = 1.0F / (s.dt * s.dt);
+    p->k.n2r1 = -2.0F * p->k.r1;
+    p->k.r2 = 1.0F / (s.h_x * s.h_x);
+    p->k.r3 = 1.0F / (s.h_y * s.h_y);
+    p->k.r4 = 1.0F / (s.h_z * s.h_z);
+
+    p->opt_kernel = env_int("FDTD_B200_KERNEL", 0);
+    p->opt_exact = env_int("FDTD_B200_EXACT", 1);
+    p->opt_fuse = env_int("FDTD_B200_FUSE_INJECT", 1);
+    p->opt_graph = env_int("FDTD_B200_GRAPH", 0);
+    p->cfg.ty = env_int("FDTD_B200_TILE_Y", 0);
+    p->cfg.tz = env_int("FDTD_B200_TILE_Z", 0);
+    p->cfg.stages = env_int("FDTD_B200_STAGES", 0);
+    p->cfg.xchunk = env_int("FDTD_B200_XCHUNK", 0);
+    p->opt_t_fuse = g_t_fuse;
+
+    cudaError_t e = cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc(&p->d_u, 3 * (size_t)p->g.lvl * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&p->d_m, (size_t)p->g.lvl * sizeof(float));
+    if (e != cudaSuccess) {
+        fdtd_b200_plan_destroy(p);
+        return (int)e;
+    }
+    *out = p;
+    return 0;
+}
+
+extern "C" int fdtd_b200_plan_create(const fdtd_b200_geometry *geo, fdtd_b200_plan **out)
+{
+    if (!geo || geo->nx < 1 || geo->ny < 1 || geo->nz < 1) return (int)cudaErrorInvalidValue;
+    PlanShape s{};
+    s.nxp = geo->nx + 2 * FDTD_HALO;
+    s.nyp = geo->ny + 2 * FDTD_HALO;
+    s.nzp = geo->nz + 2 * FDTD_HALO;
+    s.x_m = 0;
+    s.x_M = geo->nx - 1;
+    s.y_m = 0;
+    s.y_M = geo->ny - 1;
+    s.z_m = 0;
+    s.z_M = geo->nz - 1;
+    s.dt = geo->dt;
+    s.h_x = geo->h_x;
+    s.h_y = geo->h_y;
+    s.h_z = geo->h_z;
+    s.o_x = geo->o_x;
+    s.o_y = geo->o_y;
+    s.o_z = geo->o_z;
+    s.x_offset = geo->x_offset;
+    s.gx_m = 0;
+    s.gx_M = (geo->nx_global > 0 ? geo->nx_global : geo->nx) - 1;
+    if (s.x_offset < 0 || s.x_offset + geo->nx - 1 > s.gx_M) return (int)cudaErrorInvalidValue;
+    s.deviceid = geo->deviceid;
+    return plan_create_internal(s, out);
+}
+
+extern "C" int fdtd_b200_plan_destroy(fdtd_b200_plan *p)
+{
+    if (!p) return 0;
+    cudaSetDevice(p->dev);
+    plan_free_sources(p);
+    cudaFree(p->d_u);
+    cudaFree(p->d_m);
+    if (p->stream) cudaStreamDestroy(p->stream);
+    delete p;
+    return 0;
+}
+
+extern "C" float *fdtd_b200_plan_u(fdtd_b200_plan *p) { return p ? p->d_u : nullptr; }
+extern "C" float *fdtd_b200_plan_m(fdtd_b200_plan *p) { return p ? p->d_m : nullptr; }
+extern "C" size_t fdtd_b200_plan_level_elems(fdtd_b200_plan *p) { return p ? (size_t)p->g.lvl : 0; }
+extern "C" long fdtd_b200_plan_last_launches(fdtd_b200_plan *p) { return p ? p->last_launches : 0; }
+extern "C" double fdtd_b200_plan_last_kernel_seconds(fdtd_b200_plan *p) { return p ? p->last_kernel_seconds : 0.0; }
+
+extern "C" int fdtd_b200_plan_upload(fdtd_b200_plan *p, const float *h_u, const float *h_m)
+{
+    if (!p) return (int)cudaErrorInvalidValue;
+    FDTD_CHECK(cudaSetDevice(p->dev));
+    if (h_u) FDTD_CHECK(cudaMemcpyAsync(p->d_u, h_u, 3 * (size_t)p->g.lvl * sizeof(float), cudaMemcpyHostToDevice, p->stream));
+    if (h_m) FDTD_CHECK(cudaMemcpyAsync(p->d_m, h_m, (size_t)p->g.lvl * sizeof(float), cudaMemcpyHostToDevice, p->stream));
+    FDTD_CHECK(cudaStreamSynchronize(p->stream));
+    return 0;
+}
+
+extern "C" int fdtd_b200_plan_download(fdtd_b200_plan *p, float *h_u)
+{
+    if (!p || !h_u) return (int)cudaErrorInvalidValue;
+    FDTD_CHECK(cudaSetDevice(p->dev));
+    FDTD_CHECK(cudaMemcpyAsync(h_u, p->d_u, 3 * (size_t)p->g.lvl * sizeof(float), cudaMemcpyDeviceToHost, p->stream));
+    FDTD_CHECK(cudaStreamSynchronize(p->stream));
+    return 0;
+}
+
+extern "C" int fdtd_b200_plan_fill(fdtd_b200_plan *p, float u_value, float m_value)
+{
+    if (!p) return (int)cudaErrorInvalidValue;
+    FDTD_CHECK(cudaSetDevice(p->dev));
+    int rc = launch_fill(p->d_u, 3 * (size_t)p->g.lvl, u_value, p->stream);
+    if (!rc) rc = launch_fill(p->d_m, (size_t)p->g.lvl, m_value, p->stream);
+    if (rc) return rc;
+    FDTD_CHECK(cudaStreamSynchronize(p->stream));
+    return 0;
+}
+
+extern "C" int fdtd_b200_plan_fill_dense(fdtd_b200_plan *p)
+{
+    if (!p) return (int)cudaErrorInvalidValue;
+    FDTD_CHECK(cudaSetDevice(p->dev));
+    int rc = launch_fill_dense(p->d_u, p->d_m, p->g.nxp, p->g.nyp, p->g.nzp, p->shape.x_offset, p->stream);
+    if (rc) return rc;
+    FDTD_CHECK(cudaStreamSynchronize(p->stream));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------- sources
+extern "C" int fdtd_b200_plan_set_sources(fdtd_b200_plan *p, const float *src, int src_size0, int pstride,
+                                          const float *coords, int ncoords, int cstride, int p_src_m, int p_src_M)
+{
+    if (!p) return (int)cudaErrorInvalidValue;
+    FDTD_CHECK(cudaSetDevice(p->dev));
+    plan_free_sources(p);
+    // the reference's guard, openacc.cpp:113
+    if (!(src_size0 * pstride > 0 && p_src_M - p_src_m + 1 > 0) || !src || !coords) return 0;
+    if (p_src_m < 0 || p_src_M >= ncoords || p_src_M >= pstride || cstride < 3) return (int)cudaErrorInvalidValue;
+
+    const PlanShape &s = p->shape;
+    const Grid &g = p->g;
+    const bool first_slab = s.x_offset + s.x_m == s.gx_m, last_slab = s.x_offset + s.x_M == s.gx_M;
+    const int lo[3] = {s.gx_m, s.y_m, s.z_m}, hi[3] = {s.gx_M, s.y_M, s.z_M};
+    const float o[3] = {s.o_x, s.o_y, s.o_z}, h[3] = {s.h_x, s.h_y, s.h_z};
+
+    std::map<std::tuple<int, int, int>, std::vector<SourceContrib>> cells;  // ordered by (X,Y,Z); p ascending inside
+    std::vector<long long> base_idx((size_t)p_src_M + 1, -1);
+    for (int ps = p_src_m; ps <= p_src_M; ++ps) {
+        int pos[3], in_range[8];
+        float frac[3], w[8];
+        fdtd_b200_source_table(coords + (size_t)ps * cstride, o, h, lo, hi, pos, frac, w, in_range);
+        bool any = false;
+        for (int rx = 0; rx <= 1; ++rx)
+            for (int ry = 0; ry <= 1; ++ry)
+                for (int rz = 0; rz <= 1; ++rz) {
+                    const int i = rx * 4 + ry * 2 + rz;
+                    if (!in_range[i]) continue;
+                    const int X = rx + pos[0] - s.x_offset + FDTD_HALO;  // local padded plane
+                    const int Y = ry + pos[1] + FDTD_HALO, Z = rz + pos[2] + FDTD_HALO;
+                    // ownership along the slab axis: interior planes, plus the physical halo plane at a global end
+                    const bool owned = (X >= g.X0 && X < g.X1) || (first_slab && X == g.X0 - 1) || (last_slab && X == g.X1);
+                    if (!owned) continue;
+                    cells[std::make_tuple(X, Y, Z)].push_back(SourceContrib{ps, w[i]});
+                    any = true;
+                }
+        if (any)
+            base_idx[ps] = ((long long)(pos[0] - s.x_offset + FDTD_HALO) * g.nyp + (pos[1] + FDTD_HALO)) * g.nzp +
+                           (pos[2] + FDTD_HALO);
+    }
+
+    // interior cells first (sorted by plane), then the cells outside the Section0 write range ("halo" cells)
+    std::vector<SourceCell> cint, chalo;
+    std::vector<SourceContrib> contribs;
+    for (auto &kv : cells) {
+        SourceCell c;
+        std::tie(c.X, c.Y, c.Z) = kv.first;
+        c.first = (int)contribs.size();
+        c.count = (int)kv.second.size();
+        contribs.insert(contribs.end(), kv.second.begin(), kv.second.end());
+        const bool interior = c.X >= g.X0 && c.X < g.X1 && c.Y >= g.Y0 && c.Y < g.Y1 && c.Z >= g.Z0 && c.Z < g.Z1;
+        (interior ? cint : chalo).push_back(c);
+    }
+    std::vector<int> plane_off((size_t)g.nxp + 1, 0);
+    for (const SourceCell &c : cint) plane_off[c.X + 1]++;
+    for (int x = 0; x < g.nxp; ++x) plane_off[x + 1] += plane_off[x];
+    std::vector<SourceCell> all(cint);
+    all.insert(all.end(), chalo.begin(), chalo.end());
+
+    p->ncells_int = (int)cint.size();
+    p->ncells_halo = (int)chalo.size();
+    p->ncells_all = (int)all.size();
+    p->src_size0 = src_size0;
+    p->pstride = pstride;
+    p->n_mbase = p_src_M + 1;
+    FDTD_CHECK(cudaMalloc(&p->d_src, (size_t)src_size0 * pstride * sizeof(float)));
+    FDTD_CHECK(cudaMemcpy(p->d_src, src, (size_t)src_size0 * pstride * sizeof(float), cudaMemcpyHostToDevice));
+    FDTD_CHECK(cudaMalloc(&p->d_plane_off, plane_off.size() * sizeof(int)));
+    FDTD_CHECK(cudaMemcpy(p->d_plane_off, plane_off.data(), plane_off.size() * sizeof(int), cudaMemcpyHostToDevice));
+    FDTD_CHECK(cudaMalloc(&p->d_mbase, (size_t)p->n_mbase * sizeof(float)));
+    FDTD_CHECK(cudaMalloc(&p->d_base_idx, (size_t)p->n_mbase * sizeof(long long)));
+    FDTD_CHECK(cudaMemcpy(p->d_base_idx, base_idx.data(), (size_t)p->n_mbase * sizeof(long long), cudaMemcpyHostToDevice));
+    if (!all.empty()) {
+        FDTD_CHECK(cudaMalloc(&p->d_cells, all.size() * sizeof(SourceCell)));
+        FDTD_CHECK(cudaMemcpy(p->d_cells, all.data(), all.size() * sizeof(SourceCell), cudaMemcpyHostToDevice));
+        FDTD_CHECK(cudaMalloc(&p->d_contribs, contribs.size() * sizeof(SourceContrib)));
+        FDTD_CHECK(cudaMemcpy(p->d_contribs, contribs.data(), contribs.size() * sizeof(SourceContrib), cudaMemcpyHostToDevice));
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------- options
+static int *option_slot(fdtd_b200_plan *p, const char *key)
+{
+    if (!p || !key) return nullptr;
+    if (!strcmp(key, "kernel")) return &p->opt_kernel;
+    if (!strcmp(key, "exact")) return &p->opt_exact;
+    if (!strcmp(key, "fuse_inject")) return &p->opt_fuse;
+    if (!strcmp(key, "graph")) return &p->opt_graph;
+    if (!strcmp(key, "t_fuse")) return &p->opt_t_fuse;
+    if (!strcmp(key, "tile_y")) return &p->cfg.ty;
+    if (!strcmp(key, "tile_z")) return &p->cfg.tz;
+    if (!strcmp(key, "stages")) return &p->cfg.stages;
+    if (!strcmp(key, "xchunk")) return &p->cfg.xchunk;
+    return nullptr;
+}
+
+extern "C" int fdtd_b200_plan_set_option(fdtd_b200_plan *p, const char *key, int value)
+{
+    int *slot = option_slot(p, key);
+    if (!slot) return (int)cudaErrorInvalidValue;
+    *slot = value;
+    p->tma.valid = false;  // rebuilt lazily by the next run
+    return 0;
+}
+
+extern "C" int fdtd_b200_plan_get_option(fdtd_b200_plan *p, const char *key, int *value)
+{
+    if (!p || !key || !value) return (int)cudaErrorInvalidValue;
+    if (!strcmp(key, "kernel_used")) { *value = p->kernel_used; return 0; }
+    if (!strcmp(key, "tile_y_used")) { *value = p->tma.valid ? p->tma.ty : 0; return 0; }
+    if (!strcmp(key, "tile_z_used")) { *value = p->tma.valid ? p->tma.tz : 0; return 0; }
+    if (!strcmp(key, "stages_used")) { *value = p->tma.valid ? p->tma.stages : 0; return 0; }
+    if (!strcmp(key, "xchunk_used")) { *value = p->tma.valid ? p->tma.xchunk : 0; return 0; }
+    if (!strcmp(key, "ncells_fused")) { *value = p->ncells_int; return 0; }
+    if (!strcmp(key, "ncells_halo")) { *value = p->ncells_halo; return 0; }
+    int *slot = option_slot(p, key);
+    if (!slot) return (int)cudaErrorInvalidValue;
+    *value = *slot;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------- the time loop
+// One time step on [X0, X1): Section0 with the owned interior source cells fused into its epilogue,
+// then the stand-alone scatter for whatever was not fused (halo cells, or everything when fusion is
+// off).  mark(true)/mark(false) are called right before/after a scatter launch (section timers).
+template <class Mark>
+static int plan_step(fdtd_b200_plan *p, int time, Mark &&mark)
+{
+    const int t0 = ((time % 3) + 3) % 3, t1 = (((time + 2) % 3) + 3) % 3, t2 = (((time + 1) % 3) + 3) % 3;
+    const bool has_src = p->ncells_all > 0 && time >= 0 && time < p->src_size0;
+    const float *src_row = has_src ? p->d_src + (size_t)time * p->pstride : nullptr;
+
+    StepArgs a{};
+    a.u = p->d_u;
+    a.m = p->d_m;
+    a.g = p->g;
+    a.k = p->k;
+    a.t0 = t0;
+    a.t1 = t1;
+    a.t2 = t2;
+    const bool fuse = has_src && p->opt_fuse && p->ncells_int > 0;
+    if (fuse) {
+        a.sv.plane_off = p->d_plane_off;
+        a.sv.cells = p->d_cells;
+        a.sv.contribs = p->d_contribs;
+        a.sv.src_row = src_row;
+        a.sv.mbase = p->d_mbase;
+        a.sv.ncells = p->ncells_int;
+    }
+    int rc;
+    if (p->kernel_used == 2)
+        rc = launch_stencil_tma(p->tma, a, p->opt_exact != 0, p->stream);
+    else
+        rc = launch_stencil_generic(a, p->opt_exact != 0, p->stream);
+    if (rc) return rc;
+    p->last_launches++;
+
+    if (has_src) {
+        // cells [0, ncells_int) are interior (fused above unless fusion is off), the rest are halo cells
+        const int first = fuse ? p->ncells_int : 0;
+        const int count = p->ncells_all - first;
+        if (count > 0) {
+            mark(true);
+            rc = launch_scatter(p->d_u + (size_t)t2 * p->g.lvl, p->g, p->d_cells + first, count, p->d_contribs, src_row,
+                                p->d_mbase, p->stream);
+            if (rc) return rc;
+            p->last_launches++;
+            mark(false);
+        }
+    }
+    return 0;
+}
+
+extern "C" int fdtd_b200_plan_run(fdtd_b200_plan *p, int time_m, int time_M, struct profiler *timers)
+{
+    if (!p) return (int)cudaErrorInvalidValue;
+    FDTD_CHECK(cudaSetDevice(p->dev));
+    if (timers) timers->section0 = timers->section1 = 0.0;
+    p->last_launches = 0;
+    p->last_kernel_seconds = 0.0;
+    if (time_M < time_m) return 0;
+
+    // kernel choice
+    const bool can_tma = tma_supported(p->g);
+    int want = p->opt_kernel;
+    if (want == 0) want = can_tma ? 2 : 1;
+    if (want == 2 && !can_tma) return (int)cudaErrorInvalidValue;
+    if (want == 2 && !p->tma.valid) {
+        int rc = tma_plan_build(p->tma, p->d_u, p->d_m, p->g, p->cfg, p->opt_exact != 0, p->sm_count);
+        if (rc) return rc;
+    }
+    p->kernel_used = want;
+
+    if (p->ncells_all > 0) {  // m at every source's base corner (m may have been re-uploaded)
+        int rc = launch_gather_mbase(p->d_m, p->d_base_idx, p->d_mbase, p->n_mbase, p->stream);
+        if (rc) return rc;
+        p->last_launches++;
+    }
+
+    const int first_timed = time_m + FDTD_WARMUP_STEPS;  // openacc.cpp:90-92,148
+    const int ntimed = time_M >= first_timed ? time_M - first_timed + 1 : 0;
+    std::vector<cudaEvent_t> ev;
+    auto stamp = [&]() {
+        cudaEvent_t e = nullptr;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, p->stream);
+        ev.push_back(e);
+        return e;
+    };
+
+    int rc = 0;
+    cudaEvent_t e_begin = nullptr, e_end = nullptr;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> s1_spans;  // Section1 = stand-alone scatter launches only
+    for (int time = time_m; time <= time_M && !rc; ++time) {
+        if (time >= first_timed) {
+            if (!e_begin) e_begin = stamp();
+            rc = plan_step(p, time, [&](bool begin) {
+                if (begin) s1_spans.push_back({stamp(), nullptr});
+                else s1_spans.back().second = stamp();
+            });
+        } else {
+            rc = plan_step(p, time, [](bool) {});
+        }
+    }
+    if (!rc && e_begin) e_end = stamp();
+    cudaError_t es = cudaStreamSynchronize(p->stream);
+    if (!rc && es != cudaSuccess) rc = (int)es;
+    if (!rc && e_begin && e_end) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e_begin, e_end);
+        double total = ms * 1e-3, s1 = 0.0;
+        for (auto &sp : s1_spans) {
+            if (!sp.second) continue;
+            float m1 = 0.f;
+            cudaEventElapsedTime(&m1, sp.first, sp.second);
+            s1 += m1 * 1e-3;
+        }
+        if (timers) {
+            timers->section0 = total - s1;
+            timers->section1 = s1;
+        }
+        p->last_kernel_seconds = ntimed > 0 ? (total - s1) / ntimed : 0.0;
+    }
+    for (cudaEvent_t e : ev) cudaEventDestroy(e);
+    return rc;
+}

@@ -1,0 +1,49 @@
+// fdtd_plan.h -- the resident plan object behind include/fdtd_b200.h (internal).
+#pragma once
+#include "../../include/fdtd_b200.h"
+#include "fdtd_kernels.cuh"
+
+namespace fdtd {
+
+// Array shape and update extents exactly as the reference ABI passes them (unpadded, inclusive).
+struct PlanShape {
+    int nxp, nyp, nzp;
+    int x_m, x_M, y_m, y_M, z_m, z_M;  // local extents of this slab
+    float dt, h_x, h_y, h_z, o_x, o_y, o_z;
+    int x_offset;      // global index of local x = 0
+    int gx_m, gx_M;    // GLOBAL x extents (== x_m, x_M for one slab)
+    int deviceid;
+};
+
+int plan_create_internal(const PlanShape &s, fdtd_b200_plan **out);
+
+}  // namespace fdtd
+
+struct fdtd_b200_plan {
+    fdtd::PlanShape shape{};
+    int dev = 0, sm_count = 148;
+    cudaStream_t stream = nullptr;
+    fdtd::Grid g{};
+    fdtd::Coef k{};
+    float *d_u = nullptr, *d_m = nullptr;
+
+    // sources: cells [0, ncells_int) are inside the Section0 write range (fusable), the rest are halo cells
+    float *d_src = nullptr;
+    int src_size0 = 0, pstride = 1;
+    fdtd::SourceCell *d_cells = nullptr;
+    fdtd::SourceContrib *d_contribs = nullptr;
+    int *d_plane_off = nullptr;
+    float *d_mbase = nullptr;
+    long long *d_base_idx = nullptr;
+    int ncells_int = 0, ncells_halo = 0, ncells_all = 0, n_mbase = 0;
+
+    // options
+    int opt_kernel = 0, opt_exact = 1, opt_fuse = 1, opt_graph = 0, opt_t_fuse = 1;
+    fdtd::TmaConfig cfg{};
+    fdtd::TmaPlan tma{};
+    int kernel_used = 0;
+
+    // statistics of the last run
+    long last_launches = 0;
+    double last_kernel_seconds = 0.0;
+};

@@ -1,0 +1,137 @@
+// stencil_generic.cu -- Section0 for ANY extents/alignment (one point per thread, neighbour reuse
+// through L1/L2), the Section1 stand-alone scatter, and small utility kernels.
+//
+// Replaces reference cuda.cu:61-108 (stencil_update_kernel_1step) and cuda.cu:112-170 /
+// cuda_optimized.cu:241-260 (source_inject_kernel).  Unlike the reference's plain kernel the
+// thread x index walks the CONTIGUOUS z axis, and the scatter is atomics-free: one thread owns
+// one cell and adds its contributions in p_src order (the serial order of openacc.cpp:116-136).
+#include "fdtd_arith.cuh"
+#include "fdtd_kernels.cuh"
+
+namespace fdtd {
+
+template <bool EXACT>
+__global__ void __launch_bounds__(256) stencil_generic_kernel(StepArgs a)
+{
+    const int Z = a.g.Z0 + blockIdx.x * blockDim.x + threadIdx.x;
+    const int Y = a.g.Y0 + blockIdx.y * blockDim.y + threadIdx.y;
+    const int X = a.g.X0 + blockIdx.z;
+    if (Z >= a.g.Z1 || Y >= a.g.Y1) return;
+
+    const long long sy = a.g.nzp, sx = (long long)a.g.nyp * a.g.nzp;
+    const long long c = (long long)X * sx + (long long)Y * sy + Z;
+    const float *__restrict__ u0 = a.u + a.t0 * a.g.lvl;
+    const float *__restrict__ u1 = a.u + a.t1 * a.g.lvl;
+    float *__restrict__ u2 = a.u + a.t2 * a.g.lvl;
+
+    const float uc = __ldg(u0 + c);
+    const float r5 = EXACT ? __fmul_rn(FDTD_C0, uc) : FDTD_C0 * uc;
+    const float dx = axis_term<EXACT>(r5, __ldg(u0 + c - 2 * sx), __ldg(u0 + c - sx), __ldg(u0 + c + sx), __ldg(u0 + c + 2 * sx));
+    const float dy = axis_term<EXACT>(r5, __ldg(u0 + c - 2 * sy), __ldg(u0 + c - sy), __ldg(u0 + c + sy), __ldg(u0 + c + 2 * sy));
+    const float dz = axis_term<EXACT>(r5, __ldg(u0 + c - 2), __ldg(u0 + c - 1), __ldg(u0 + c + 1), __ldg(u0 + c + 2));
+    float v = leapfrog<EXACT>(uc, dx, dy, dz, __ldg(u1 + c), __ldg(a.m + c), a.k);
+
+    if (a.sv.ncells > 0) {  // fused Section1: the owner of a source cell adds its contributions
+        const int c0 = a.sv.plane_off[X], c1 = a.sv.plane_off[X + 1];
+        for (int i = c0; i < c1; ++i) {
+            const SourceCell cell = a.sv.cells[i];
+            if (cell.Y == Y && cell.Z == Z) v = apply_cell(v, cell, a.sv);
+        }
+    }
+    u2[c] = v;
+}
+
+int launch_stencil_generic(const StepArgs &a, bool exact, cudaStream_t stream)
+{
+    const int nz = a.g.Z1 - a.g.Z0, ny = a.g.Y1 - a.g.Y0, nx = a.g.X1 - a.g.X0;
+    if (nx <= 0 || ny <= 0 || nz <= 0) return 0;
+    dim3 block(64, 4, 1);
+    if (nz <= 32) block = dim3(32, 8, 1);
+    dim3 grid((nz + block.x - 1) / block.x, (ny + block.y - 1) / block.y, nx);
+    if (grid.y > 65535 || grid.z > 65535) return (int)cudaErrorInvalidValue;
+    if (exact)
+        stencil_generic_kernel<true><<<grid, block, 0, stream>>>(a);
+    else
+        stencil_generic_kernel<false><<<grid, block, 0, stream>>>(a);
+    return (int)cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------- Section1 scatter
+__global__ void scatter_kernel(float *__restrict__ u2, Grid g, const SourceCell *__restrict__ cells, int ncells,
+                               SourceView sv)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ncells) return;
+    const SourceCell cell = cells[i];
+    const long long c = ((long long)cell.X * g.nyp + cell.Y) * g.nzp + cell.Z;
+    u2[c] = apply_cell(u2[c], cell, sv);
+}
+
+int launch_scatter(float *u_level, const Grid &g, const SourceCell *cells, int ncells,
+                   const SourceContrib *contribs, const float *src_row, const float *mbase,
+                   cudaStream_t stream)
+{
+    if (ncells <= 0) return 0;
+    SourceView sv{};
+    sv.contribs = contribs;
+    sv.src_row = src_row;
+    sv.mbase = mbase;
+    sv.ncells = ncells;
+    scatter_kernel<<<(ncells + 127) / 128, 128, 0, stream>>>(u_level, g, cells, ncells, sv);
+    return (int)cudaGetLastError();
+}
+
+__global__ void gather_mbase_kernel(const float *__restrict__ m, const long long *__restrict__ idx,
+                                    float *__restrict__ out, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = idx[i] >= 0 ? m[idx[i]] : 1.0f;
+}
+
+int launch_gather_mbase(const float *m, const long long *base_idx, float *mbase, int n, cudaStream_t stream)
+{
+    if (n <= 0) return 0;
+    gather_mbase_kernel<<<(n + 127) / 128, 128, 0, stream>>>(m, base_idx, mbase, n);
+    return (int)cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------- fills
+__global__ void fill_kernel(float4 *p4, float *p, size_t n4, size_t n, float v)
+{
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const float4 v4 = make_float4(v, v, v, v);
+    for (size_t i = t; i < n4; i += stride) p4[i] = v4;
+    for (size_t i = n4 * 4 + t; i < n; i += stride) p[i] = v;
+}
+
+int launch_fill(float *p, size_t n, float v, cudaStream_t stream)
+{
+    if (n == 0) return 0;
+    const size_t n4 = (((uintptr_t)p & 15) == 0) ? n / 4 : 0;
+    fill_kernel<<<148 * 8, 256, 0, stream>>>((float4 *)p, p, n4, n, v);
+    return (int)cudaGetLastError();
+}
+
+// Dense parity field of reference main.cpp:525-532: m = 1.5, u[0] = u[1] = sin(i*0.001f)*10+100 over
+// the whole padded volume (halos included), i = GLOBAL linear index; u[2] = 0.
+__global__ void fill_dense_kernel(float *__restrict__ u, float *__restrict__ m, size_t volp, size_t goff)
+{
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < volp; i += stride) {
+        const float val = __fadd_rn(__fmul_rn(sinf(__fmul_rn((float)(i + goff), 0.001f)), 10.0f), 100.0f);
+        m[i] = 1.5f;
+        u[i] = val;
+        u[volp + i] = val;
+        u[2 * volp + i] = 0.0f;
+    }
+}
+
+int launch_fill_dense(float *u, float *m, int nxp, int nyp, int nzp, long long x_plane_offset, cudaStream_t stream)
+{
+    const size_t volp = (size_t)nxp * nyp * nzp;
+    fill_dense_kernel<<<148 * 8, 256, 0, stream>>>(u, m, volp, (size_t)x_plane_offset * nyp * nzp);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace fdtd

@@ -1,0 +1,248 @@
+"""GPU parity tests (run on the B200 box with `-m gpu`): the CUDA path, called through the C ABI
+(Kernel_B200 / Kernel_CUDA_Optimized / resident plans), against the CPU oracle on the same inputs and
+against the golden fixtures generated from the unmodified reference.
+
+Bars (BASELINE.json north_star): exact mode is BIT-IDENTICAL to the oracle (0 ulp); contracted
+mode must satisfy relative L2 < 1e-4 (README.md:33); source indices/weights are bit-exact.
+"""
+import hashlib
+
+import numpy as np
+import pytest
+
+from conftest import bench_inputs, bits_equal
+
+pytestmark = pytest.mark.gpu
+
+REL_L2_TOL = 1e-4  # the reference's own criterion, README.md:33
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def run_abi(pkg, u, m, src, crd, *, h=0.1, dt=1e-3, time_m=0, time_M=None, p_src_m=0, p_src_M=None, extents=None,
+            entry="Kernel_B200"):
+    nxp, nyp, nzp = u.shape[1:]
+    if extents is None:
+        extents = (0, nxp - 9, 0, nyp - 9, 0, nzp - 9)
+    x_m, x_M, y_m, y_M, z_m, z_M = extents
+    if src is None:
+        p_src_M = -1
+    elif p_src_M is None:
+        p_src_M = crd.shape[0] - 1
+    if time_M is None:
+        time_M = src.shape[0] - 1
+    t = pkg.Profiler(0.0, 0.0)
+    rc = getattr(pkg, entry)(m, src, crd, u, x_M, x_m, y_M, y_m, z_M, z_m, dt, h, h, h, 0.0, 0.0, 0.0, p_src_M, p_src_m,
+                             time_M, time_m, 0, 1, t)
+    assert rc == 0, f"{entry} returned cudaError {rc}"
+    return t
+
+
+def run_plan(pkg, u, m, src, crd, *, h=0.1, time_m=0, time_M=None, options=None, p_src_m=0, p_src_M=None):
+    nxp, nyp, nzp = u.shape[1:]
+    with pkg.Plan(nxp - 8, nyp - 8, nzp - 8, h=h, deviceid=0) as p:
+        for k, v in (options or {}).items():
+            p.set_option(k, v)
+        p.upload(u, m)
+        if src is not None:
+            p.set_sources(src, crd, p_src_m, p_src_M)
+            if time_M is None:
+                time_M = src.shape[0] - 1
+        t = p.run(time_m, time_M)
+        p.download(u)
+        info = {k: p.get_option(k) for k in ("kernel_used", "tile_y_used", "tile_z_used", "xchunk_used", "ncells_fused",
+                                              "ncells_halo")}
+        info["launches"] = p.last_launches
+    return t, info
+
+
+# ------------------------------------------------------------------ golden fixtures through the reference ABI
+@pytest.mark.parametrize("name", ["bench64_s1", "bench64_s64", "bench32_s27", "bench256_s1"])
+def test_benchmark_config_matches_golden(pkg, oracle, golden, name):
+    meta, arrs = golden
+    g = meta[name]
+    u, m, src, crd = bench_inputs(oracle, g["n"], g["T"], g["S"])
+    t = run_abi(pkg, u, m, src, crd, entry="Kernel_CUDA_Optimized")
+    assert sha(u) == g["sha256"], "not bit-identical to the reference build"
+    assert float(np.abs(u).max()) == g["max_abs"]
+    assert t.section0 > 0 and t.section1 == 0.0  # every source cell fused into Section0
+
+
+def test_dense_correctness_config_matches_golden(pkg, oracle, golden):
+    """main.cpp:525-570: sin field over the whole padded volume (non-zero halos), h = 1, no sources."""
+    meta, arrs = golden
+    u, m = oracle.fill_dense(16, 16, 16)
+    run_abi(pkg, u, m, None, None, h=1.0, time_M=49)
+    assert bits_equal(u, arrs["dense16_u"])
+    u, m = oracle.fill_dense(32, 32, 32)
+    run_abi(pkg, u, m, None, None, h=1.0, time_M=49)
+    assert sha(u) == meta["dense32"]["sha256"]
+
+
+def test_random_fields_and_boundary_sources_match_golden(pkg, golden):
+    meta, arrs = golden
+    u = arrs["rand16_u_in"].copy()
+    run_abi(pkg, u, arrs["rand16_m"], arrs["rand16_src"], arrs["rand16_crd"])
+    assert bits_equal(u, arrs["rand16_u_out"])
+    # non-cubic, n % 4 != 0 (generic kernel), ring phase 4, source sub-range
+    g = meta["odd"]
+    u = arrs["odd_u_in"].copy()
+    run_abi(pkg, u, arrs["odd_m"], arrs["odd_src"], arrs["odd_crd"], time_m=g["time_m"], time_M=g["time_M"],
+            p_src_m=g["p_src_m"], p_src_M=g["p_src_M"])
+    assert bits_equal(u, arrs["odd_u_out"])
+
+
+# ------------------------------------------------------------------ kernel variants against the oracle
+def random_case(rng, shape, T, S):
+    nx, ny, nz = shape
+    u = rng.uniform(-1, 1, (3, nx + 8, ny + 8, nz + 8)).astype(np.float32)
+    m = rng.uniform(0.5, 3.0, (nx + 8, ny + 8, nz + 8)).astype(np.float32)
+    src = rng.uniform(-20, 20, (T, S)).astype(np.float32)
+    crd = (rng.uniform(-0.03, 1.03, (S, 3)) * (np.array(shape, np.float32) - 1) * np.float32(0.1)).astype(np.float32)
+    if S >= 3:
+        crd[1] = crd[0]  # coincident sources: per-cell ordering
+    return u, m, src, crd
+
+
+TILES = [(32, 64, 6), (32, 64, 8), (16, 64, 5), (16, 64, 6), (16, 128, 6), (16, 128, 8), (8, 128, 5), (8, 128, 6),
+         (8, 64, 5), (8, 64, 6), (16, 32, 5), (16, 32, 6), (8, 32, 6), (32, 32, 6)]
+
+
+@pytest.mark.parametrize("ty,tz,stages", TILES)
+def test_tma_variants_bit_exact(pkg, oracle, ty, tz, stages):
+    """Every tile instantiation, on a grid that is NOT a multiple of the tile (ragged edges in y and z),
+    several x chunks, random m, sources inside / on the boundary / outside."""
+    rng = np.random.default_rng(100 + ty + tz + stages)
+    shape = (21, 44, 72)
+    u, m, src, crd = random_case(rng, shape, 8, 6)
+    ref = u.copy()
+    oracle.run(ref, m, src, crd, impl="port")
+    t, info = run_plan(pkg, u, m, src, crd, options={"kernel": 2, "tile_y": ty, "tile_z": tz, "stages": stages, "xchunk": 8})
+    assert info["kernel_used"] == 2 and (info["tile_y_used"], info["tile_z_used"]) == (ty, tz)
+    assert bits_equal(u, ref)
+
+
+@pytest.mark.parametrize("kernel", [1, 2])
+@pytest.mark.parametrize("fuse", [0, 1])
+def test_fused_and_standalone_injection_agree(pkg, oracle, kernel, fuse):
+    rng = np.random.default_rng(11)
+    u, m, src, crd = random_case(rng, (20, 24, 32), 12, 9)
+    ref = u.copy()
+    oracle.run(ref, m, src, crd, impl="port")
+    t, info = run_plan(pkg, u, m, src, crd, options={"kernel": kernel, "fuse_inject": fuse})
+    assert bits_equal(u, ref)
+    assert info["ncells_fused"] > 0
+    if fuse == 0:
+        assert t.section1 > 0  # the stand-alone scatter is timed as Section1
+
+
+@pytest.mark.parametrize("kernel", [1, 2])
+def test_contracted_arithmetic_within_tolerance(pkg, oracle, kernel):
+    """exact = 0 (FMA-contracted leapfrog form of cuda.cu:105): relative L2 < 1e-4 (README.md:33)."""
+    u, m = oracle.fill_dense(32, 32, 32)
+    ref = u.copy()
+    oracle.run(ref, m, time_M=49, h=1.0, impl="port")
+    run_plan(pkg, u, m, None, None, h=1.0, time_M=49, options={"kernel": kernel, "exact": 0})
+    err = oracle.rel_l2(u, ref)
+    assert err < REL_L2_TOL, err
+    assert np.abs(u - ref).max() <= 1e-3 * np.abs(ref).max()
+    # and on the benchmark config (spiky field, many denormals: no flush-to-zero allowed)
+    u, m, src, crd = bench_inputs(oracle, 64, 50, 1)
+    ref = u.copy()
+    oracle.run(ref, m, src, crd, impl="port")
+    run_plan(pkg, u, m, src, crd, options={"kernel": kernel, "exact": 0})
+    assert oracle.rel_l2(u, ref) < REL_L2_TOL
+    assert np.abs(u - ref).max() <= 1e-5 * np.abs(ref).max()
+    den = (np.abs(ref) < np.finfo(np.float32).tiny) & (ref != 0)
+    assert den.any() and np.count_nonzero(u[den]) > 0.9 * den.sum()  # denormals survive
+
+
+@pytest.mark.parametrize("shape", [(8, 8, 8), (5, 9, 3), (33, 17, 65), (12, 100, 36), (1, 4, 4), (64, 8, 132)])
+def test_odd_and_ragged_extents(pkg, oracle, shape):
+    rng = np.random.default_rng(sum(shape))
+    u, m, src, crd = random_case(rng, shape, 7, 4)
+    ref = u.copy()
+    oracle.run(ref, m, src, crd, impl="port")
+    run_abi(pkg, u, m, src, crd)
+    assert bits_equal(u, ref)
+
+
+@pytest.mark.parametrize("time_m", [0, 1, 2, 7])
+def test_ring_phase_and_restart(pkg, oracle, time_m):
+    """Arbitrary time_m (ring phase time_m % 3) and a run split in two calls (restartability)."""
+    rng = np.random.default_rng(5)
+    u, m, src, crd = random_case(rng, (16, 16, 16), 20, 3)
+    ref = u.copy()
+    oracle.run(ref, m, src, crd, impl="port", time_m=time_m, time_M=19)
+    a = u.copy()
+    run_abi(pkg, a, m, src, crd, time_m=time_m, time_M=19)
+    assert bits_equal(a, ref)
+    b = u.copy()
+    run_abi(pkg, b, m, src, crd, time_m=time_m, time_M=11)
+    run_abi(pkg, b, m, src, crd, time_m=12, time_M=19)
+    assert bits_equal(b, ref)
+
+
+def test_sub_extents_leave_everything_else_untouched(pkg, oracle):
+    """x_m..z_M narrower than the arrays: only that box is written (plus in-range source corners)."""
+    rng = np.random.default_rng(9)
+    u, m, src, crd = random_case(rng, (24, 24, 24), 6, 3)
+    ext = (4, 19, 0, 23, 8, 15)
+    ref = u.copy()
+    oracle.run(ref, m, src, crd, impl="port", extents=ext)
+    run_abi(pkg, u, m, src, crd, extents=ext)
+    assert bits_equal(u, ref)
+
+
+def test_no_sources_and_short_runs(pkg, oracle):
+    rng = np.random.default_rng(2)
+    u, m, _, _ = random_case(rng, (16, 16, 16), 1, 1)
+    for T in (1, 3, 5, 6):
+        a, ref = u.copy(), u.copy()
+        oracle.run(ref, m, time_M=T - 1, impl="port")
+        t = run_abi(pkg, a, m, None, None, time_M=T - 1)
+        assert bits_equal(a, ref)
+        assert (t.section0 > 0) == (T > 5) and t.section1 == 0  # first min(5,T) steps are untimed
+    # empty extents are rejected like cuda_optimized.cu:347, arrays untouched
+    a = u.copy()
+    t = pkg.Profiler(1.0, 1.0)
+    rc = pkg.Kernel_B200(m, None, None, a, -1, 0, 15, 0, 15, 0, 1e-3, .1, .1, .1, 0, 0, 0, -1, 0, 3, 0, 0, 1, t)
+    assert rc == 1 and bits_equal(a, u) and t.section0 == 0.0
+
+
+# ------------------------------------------------------------------ full-size properties (no CPU oracle at this size)
+def test_512_properties(pkg, oracle, golden):
+    """BASELINE configs[2] (512^3, T=50, 1 source): size-independent properties.
+    * the wavefield support stays inside the low 168^3 corner, and that corner is bit-identical to the
+      oracle run on a 160^3 grid with the same source (the stencil is local, nothing reaches an edge);
+    * linearity of the operator in the source amplitude (2 x src -> 2 x u, exact in binary fp);
+    * first-source index/fraction bits match the survey's known answer (127, 0x3f400080)."""
+    n, T = 512, 50
+    src, crd = pkg.fill_ricker(T, 1), pkg.fill_source_coords(1, n, n, n)
+    pos, frac, _, _ = pkg.source_table(crd[0], (0, 0, 0), (0.1,) * 3, (0, 0, 0), (n - 1,) * 3)
+    assert pos.tolist() == [127] * 3 and frac.view(np.uint32).tolist() == [0x3f400080] * 3
+    with pkg.Plan(n, n, n, deviceid=0) as p:
+        p.fill(0.0, 1.5)
+        p.set_sources(src, crd)
+        t = p.run(0, T - 1)
+        u = p.download()
+        assert p.get_option("kernel_used") == 2
+        p.fill(0.0, 1.5)
+        p.set_sources(2 * src, crd)
+        p.run(0, T - 1)
+        u2 = p.download()
+    assert t.section0 > 0
+    assert bits_equal(u2, 2 * u)
+    # window: the source sits at cell 127.75 and the support radius after 50 steps is < 30 cells, so a
+    # 160^3 oracle run with the SAME physical coordinates (same pos/frac bits) reproduces the low corner
+    w = 160
+    sub_u = np.zeros((3, w + 8, w + 8, w + 8), np.float32)
+    sub_m = np.full((w + 8,) * 3, 1.5, np.float32)
+    oracle.run(sub_u, sub_m, src, crd, impl="port", threads=8)
+    assert bits_equal(u[:, :w + 8, :w + 8, :w + 8], sub_u)
+    outside = u.copy()
+    outside[:, :w + 8, :w + 8, :w + 8] = 0
+    assert not outside.any()
+    assert abs(float(np.abs(u).max()) - 0.116841748) < 1e-8  # SURVEY 8c known answer at n = 512

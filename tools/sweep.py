@@ -1,0 +1,62 @@
+#!/usr/bin/env python
+"""Tile / stage / x-chunk sweep of the streaming kernel on one GPU (tuning aid, not a bench).
+
+    python tools/sweep.py --n 512 --steps 30 > gpurun_out/sweep_512.txt
+"""
+import argparse
+import importlib
+import itertools
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+pkg = importlib.import_module("accelerated-3d-acoustic-fdtd-kernel_b200")
+
+TILES = [(16, 64, 6), (16, 64, 5), (32, 64, 6), (32, 64, 8), (16, 128, 6), (16, 128, 8), (8, 128, 6), (8, 128, 5),
+         (8, 64, 6), (8, 64, 5), (16, 32, 6), (16, 32, 5), (8, 32, 6), (32, 32, 6)]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--n", type=int, default=512)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--xchunks", type=str, default="0")
+    ap.add_argument("--exact", type=str, default="1,0")
+    ap.add_argument("--tiles", type=str, default="")
+    ap.add_argument("--generic", action="store_true")
+    a = ap.parse_args()
+    n, T = a.n, a.steps + 5
+    tiles = TILES if not a.tiles else [tuple(int(x) for x in t.split("x")) for t in a.tiles.split(",")]
+    src, crd = pkg.fill_ricker(T, 1), pkg.fill_source_coords(1, n, n, n)
+    with pkg.Plan(n, n, n, deviceid=0) as p:
+        p.set_sources(src, crd)
+        rows = []
+        if a.generic:
+            for exact in (1, 0):
+                p.fill(0.0, 1.5)
+                p.set_option("kernel", 1)
+                p.set_option("exact", exact)
+                t = p.run(0, T - 1)
+                g = n ** 3 * a.steps / (t.section0 + t.section1) / 1e9
+                print(f"generic exact={exact}: {g:8.1f} Gpts/s  {16 * g / 6551.7:6.3f} of HBM", flush=True)
+        for (ty, tz, st), xc, exact in itertools.product(tiles, [int(x) for x in a.xchunks.split(",")],
+                                                          [int(x) for x in a.exact.split(",")]):
+            p.fill(0.0, 1.5)
+            for k, v in (("kernel", 2), ("exact", exact), ("tile_y", ty), ("tile_z", tz), ("stages", st), ("xchunk", xc)):
+                p.set_option(k, v)
+            try:
+                t = p.run(0, T - 1)
+            except pkg.FdtdError as e:
+                print(f"tile {ty}x{tz} s{st} xc{xc} exact={exact}: {e}", flush=True)
+                continue
+            g = n ** 3 * a.steps / (t.section0 + t.section1) / 1e9
+            rows.append((g, ty, tz, st, p.get_option("xchunk_used"), exact))
+            print(f"tile {ty:3d}x{tz:3d} s{st} xchunk {rows[-1][4]:4d} exact={exact}: {g:8.1f} Gpts/s  "
+                  f"{16 * g / 6551.7:6.3f} of HBM  ({p.last_kernel_seconds * 1e6:8.1f} us/step)", flush=True)
+    rows.sort(reverse=True)
+    print("best:", rows[:5])
+
+
+if __name__ == "__main__":
+    main()

@@ -36,10 +36,14 @@ __device__ __forceinline__ float leapfrog(float c, float dx, float dy, float dz,
         // dt*dt*( r2*dx + r3*dy + r4*dz - ((-2*r1)*u0 + r1*u1)*m ) / m
         const float lap = __fadd_rn(__fadd_rn(__fmul_rn(k.r2, dx), __fmul_rn(k.r3, dy)), __fmul_rn(k.r4, dz));
         const float d = __fmul_rn(__fadd_rn(__fmul_rn(k.n2r1, c), __fmul_rn(k.r1, u1)), m);
-        return __fdiv_rn(__fmul_rn(k.dt2, __fsub_rn(lap, d)), m);
+        const float num = __fmul_rn(k.dt2, __fsub_rn(lap, d));
+        // (+-0)/m == (+-0)*m for finite m != 0: skip the IEEE division where the field is still zero
+        // (its FCHK guard sends zero dividends to the slow path); warp-uniform in quiescent regions.
+        if (num == 0.0f) return __fmul_rn(num, m);
+        return __fdiv_rn(num, m);
     } else {
         const float lap = fmaf(k.r4, dz, fmaf(k.r3, dy, k.r2 * dx));
-        return fmaf(2.0f, c, -u1) + __fdiv_rn(k.dt2 * lap, m);
+        return fmaf(2.0f, c, -u1) + __fdividef(k.dt2 * lap, m);
     }
 }
 

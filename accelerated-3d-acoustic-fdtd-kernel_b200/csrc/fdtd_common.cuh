@@ -21,6 +21,8 @@ struct Coef {
     float r1;    // 1/(dt*dt)
     float n2r1;  // -2.0f*r1
     float r2, r3, r4;  // 1/h_x^2, 1/h_y^2, 1/h_z^2
+    // contracted form only: dt2*r{2,3,4}*{4/3, -1/12} per axis and dt2*(r2+r3+r4)*(-5/2)
+    float fx1, fx2, fy1, fy2, fz1, fz2, f0;
 };
 
 // One grid cell that receives source contributions (padded local coordinates).

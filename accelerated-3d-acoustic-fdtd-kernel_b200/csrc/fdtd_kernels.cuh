@@ -20,14 +20,15 @@ int launch_stencil_generic(const StepArgs &a, bool exact, cudaStream_t stream);
 // --- 2.5D x-streaming kernel: TMA -> mbarrier ring in shared memory -> register queue along x.
 struct TmaConfig {
     int ty = 0, tz = 0;  // (y,z) tile; 0 = auto
-    int stages = 0;      // halo-plane ring depth S0 (centre ring has S0-2 slots)
+    int rows = 0;        // y rows per consumer thread (1, 2 or 4); 0 = auto
+    int stages = 0;      // halo-plane ring depth (5 or 10); 0 = 5
     int xchunk = 0;      // x planes per CTA; 0 = auto
 };
 struct TmaPlan {         // built once per (arrays, config): tensor maps + launch shape
     alignas(64) CUtensorMap map_halo;  // u as (z,y,x,t), box (tz+8, ty+4, 1, 1)
     alignas(64) CUtensorMap map_ctr;   // u as (z,y,x,t), box (tz, ty, 1, 1)
     alignas(64) CUtensorMap map_m;     // m as (z,y,x),   box (tz, ty, 1)
-    int ty, tz, stages, xchunk;
+    int ty, tz, rows, stages, xchunk;
     int variant;         // index into the instantiation table
     size_t smem_bytes;
     bool valid = false;

@@ -116,6 +116,13 @@ int fdtd::plan_create_internal(const PlanShape &s, fdtd_b200_plan **out)
     p->k.r2 = 1.0F / (s.h_x * s.h_x);
     p->k.r3 = 1.0F / (s.h_y * s.h_y);
     p->k.r4 = 1.0F / (s.h_z * s.h_z);
+    p->k.fx1 = p->k.dt2 * p->k.r2 * 1.333333330F;
+    p->k.fx2 = p->k.dt2 * p->k.r2 * -8.33333333e-2F;
+    p->k.fy1 = p->k.dt2 * p->k.r3 * 1.333333330F;
+    p->k.fy2 = p->k.dt2 * p->k.r3 * -8.33333333e-2F;
+    p->k.fz1 = p->k.dt2 * p->k.r4 * 1.333333330F;
+    p->k.fz2 = p->k.dt2 * p->k.r4 * -8.33333333e-2F;
+    p->k.f0 = p->k.dt2 * (p->k.r2 + p->k.r3 + p->k.r4) * -2.50F;
 
     p->opt_kernel = env_int("FDTD_B200_KERNEL", 0);
     p->opt_exact = env_int("FDTD_B200_EXACT", 1);
@@ -123,6 +130,7 @@ int fdtd::plan_create_internal(const PlanShape &s, fdtd_b200_plan **out)
     p->opt_graph = env_int("FDTD_B200_GRAPH", 0);
     p->cfg.ty = env_int("FDTD_B200_TILE_Y", 0);
     p->cfg.tz = env_int("FDTD_B200_TILE_Z", 0);
+    p->cfg.rows = env_int("FDTD_B200_ROWS", 0);
     p->cfg.stages = env_int("FDTD_B200_STAGES", 0);
     p->cfg.xchunk = env_int("FDTD_B200_XCHUNK", 0);
     p->opt_t_fuse = g_t_fuse;
@@ -317,6 +325,7 @@ static int *option_slot(fdtd_b200_plan *p, const char *key)
     if (!strcmp(key, "t_fuse")) return &p->opt_t_fuse;
     if (!strcmp(key, "tile_y")) return &p->cfg.ty;
     if (!strcmp(key, "tile_z")) return &p->cfg.tz;
+    if (!strcmp(key, "rows")) return &p->cfg.rows;
     if (!strcmp(key, "stages")) return &p->cfg.stages;
     if (!strcmp(key, "xchunk")) return &p->cfg.xchunk;
     return nullptr;
@@ -337,6 +346,7 @@ extern "C" int fdtd_b200_plan_get_option(fdtd_b200_plan *p, const char *key, int
     if (!strcmp(key, "kernel_used")) { *value = p->kernel_used; return 0; }
     if (!strcmp(key, "tile_y_used")) { *value = p->tma.valid ? p->tma.ty : 0; return 0; }
     if (!strcmp(key, "tile_z_used")) { *value = p->tma.valid ? p->tma.tz : 0; return 0; }
+    if (!strcmp(key, "rows_used")) { *value = p->tma.valid ? p->tma.rows : 0; return 0; }
     if (!strcmp(key, "stages_used")) { *value = p->tma.valid ? p->tma.stages : 0; return 0; }
     if (!strcmp(key, "xchunk_used")) { *value = p->tma.valid ? p->tma.xchunk : 0; return 0; }
     if (!strcmp(key, "ncells_fused")) { *value = p->ncells_int; return 0; }

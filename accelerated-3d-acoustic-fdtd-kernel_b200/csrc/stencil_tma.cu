@@ -23,6 +23,7 @@
 #include "fdtd_kernels.cuh"
 
 #include <cudaTypedefs.h>
+#include <math.h>
 #include <stdio.h>
 
 namespace fdtd {
@@ -84,53 +85,79 @@ __device__ __forceinline__ float4 lds128(const float *p) { return *reinterpret_c
 __device__ __forceinline__ float2 lds64(const float *p) { return *reinterpret_cast<const float2 *>(p); }
 
 // ---------------------------------------------------------------------------- geometry of one variant
-template <int TY, int TZ, int S0>
+// S0_ = halo-plane ring depth; the plane loop is unrolled by S0_ and the register queue has period 5,
+// so S0_ must be a multiple of 5 (5: two stages of prefetch, 10: seven).
+template <int TY, int TZ, int RY, int S0_>
 struct TileShape {
+    static constexpr int S0 = S0_;
+    static_assert(S0_ % 5 == 0, "ring depth must be a multiple of the queue period");
+    static constexpr int S1 = S0 - 2;               // centre-ring slots
     static constexpr int ZQ = TZ / 4;               // float4 columns per row
-    static constexpr int NC = TY * ZQ;              // consumer threads
+    static constexpr int NC = (TY / RY) * ZQ;       // consumer threads: RY rows x 4 z each
     static constexpr int NCW = NC / 32;             // consumer warps
     static constexpr int NT = NC + 32;              // + one producer warp
-    static constexpr int S1 = S0 - 2;               // centre-ring slots
     static constexpr int HP = TZ + 8;               // halo-tile pitch (floats)
     static constexpr int HROWS = TY + 4;
     static constexpr int HBYTES = HROWS * HP * 4;   // bytes one halo box delivers
     static constexpr int HSLOT = (HBYTES + 127) / 128 * 128;
     static constexpr int CBYTES = TY * TZ * 4;      // bytes one centre box delivers
     static constexpr int SMEM = S0 * HSLOT + 2 * S1 * CBYTES + 2 * S0 * 8;
-    static_assert(TZ % 4 == 0 && NC % 32 == 0, "tile must give whole warps of float4 columns");
-    static_assert(S0 >= 5, "ring must hold stages j+2..j+4 plus prefetch");
+    static_assert(TZ % 4 == 0 && TY % RY == 0 && NC % 32 == 0, "tile must give whole warps of float4 columns");
+    static_assert(NT <= 1024, "too many threads");
     static_assert(CBYTES % 128 == 0, "centre slots must stay 128-byte aligned");
 };
 
+// One output point.  x*/y*/z* are the radius-2 neighbours along each axis.
 template <bool EXACT>
-__device__ __forceinline__ float point(float c, float r_xm2, float r_xm1, float r_xp1, float r_xp2, float ym2,
-                                       float ym1, float yp1, float yp2, float zm2, float zm1, float zp1, float zp2,
-                                       float u1, float m, const Coef &k)
+__device__ __forceinline__ float point(float c, float xm2, float xm1, float xp1, float xp2, float ym2, float ym1,
+                                       float yp1, float yp2, float zm2, float zm1, float zp1, float zp2, float u1,
+                                       float m, const Coef &k)
 {
-    const float r5 = EXACT ? __fmul_rn(FDTD_C0, c) : FDTD_C0 * c;
-    const float dx = axis_term<EXACT>(r5, r_xm2, r_xm1, r_xp1, r_xp2);
-    const float dy = axis_term<EXACT>(r5, ym2, ym1, yp1, yp2);
-    const float dz = axis_term<EXACT>(r5, zm2, zm1, zp1, zp2);
-    return leapfrog<EXACT>(c, dx, dy, dz, u1, m, k);
+    if (EXACT) {
+        const float r5 = __fmul_rn(FDTD_C0, c);
+        const float dx = axis_term<true>(r5, xm2, xm1, xp1, xp2);
+        const float dy = axis_term<true>(r5, ym2, ym1, yp1, yp2);
+        const float dz = axis_term<true>(r5, zm2, zm1, zp1, zp2);
+        return leapfrog<true>(c, dx, dy, dz, u1, m, k);
+    } else {
+        // minimal-operation form: dt^2*lap accumulated with pre-multiplied coefficients, one MUFU.RCP
+        float acc = k.f0 * c;
+        acc = fmaf(k.fx2, xm2 + xp2, acc);
+        acc = fmaf(k.fx1, xm1 + xp1, acc);
+        acc = fmaf(k.fy2, ym2 + yp2, acc);
+        acc = fmaf(k.fy1, ym1 + yp1, acc);
+        acc = fmaf(k.fz2, zm2 + zp2, acc);
+        acc = fmaf(k.fz1, zm1 + zp1, acc);
+        float rm;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rm) : "f"(m));
+        return fmaf(acc, rm, fmaf(2.0f, c, -u1));
+    }
 }
 
-template <int TY, int TZ, int S0, bool EXACT, int MINB>
-__global__ void __launch_bounds__(TileShape<TY, TZ, S0>::NT, MINB)
+template <int I>
+__device__ __forceinline__ float f4get(const float4 &v)
+{
+    return I == 0 ? v.x : I == 1 ? v.y : I == 2 ? v.z : v.w;
+}
+
+template <int TY, int TZ, int RY, int NS, bool EXACT, int MINB>
+__global__ void __launch_bounds__(TileShape<TY, TZ, RY, NS>::NT, MINB)
     stencil_tma_kernel(const __grid_constant__ TmaArgs a)
 {
-    using T = TileShape<TY, TZ, S0>;
+    using T = TileShape<TY, TZ, RY, NS>;
+    constexpr int S0 = T::S0, S1 = T::S1;
     extern __shared__ __align__(1024) unsigned char smem[];
     float *sH = reinterpret_cast<float *>(smem);
     float *sU1 = reinterpret_cast<float *>(smem + S0 * T::HSLOT);
-    float *sM = sU1 + T::S1 * TY * TZ;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + S0 * T::HSLOT + 2 * T::S1 * T::CBYTES);
+    float *sM = sU1 + S1 * TY * TZ;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + S0 * T::HSLOT + 2 * S1 * T::CBYTES);
     const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + S0);
 
     const Grid &g = a.s.g;
     const int tz = blockIdx.x % a.tiles_z, ty = blockIdx.x / a.tiles_z;
     const int Xa = g.X0 + blockIdx.y * a.xchunk;
     const int Xb = min(g.X1, Xa + a.xchunk);
-    const int np = Xb - Xa;        // output planes of this CTA (>= 1 by construction)
+    const int np = Xb - Xa;         // output planes of this CTA (>= 1 by construction)
     const int Yt = g.Y0 + ty * TY;  // padded origin of the tile
     const int Zt = g.Z0 + tz * TZ;
 
@@ -157,7 +184,7 @@ __global__ void __launch_bounds__(TileShape<TY, TZ, S0>::NT, MINB)
                 if (ctr) {
                     tma_load_4d(smem_u32(sU1) + cslot * T::CBYTES, &a.map_ctr, bar, Zt, Yt, Xa + s - 4, a.s.t1);
                     tma_load_3d(smem_u32(sM) + cslot * T::CBYTES, &a.map_m, bar, Zt, Yt, Xa + s - 4);
-                    if (++cslot == T::S1) cslot = 0;
+                    if (++cslot == S1) cslot = 0;
                 }
                 if (++slot == S0) {
                     slot = 0;
@@ -169,87 +196,121 @@ __global__ void __launch_bounds__(TileShape<TY, TZ, S0>::NT, MINB)
     }
 
     // ---------------------------------------------------------------------- consumers
-    const int zq = threadIdx.x % T::ZQ, yy = threadIdx.x / T::ZQ;
+    const int zq = threadIdx.x % T::ZQ, yr = threadIdx.x / T::ZQ;
     const int lane = threadIdx.x & 31;
-    const int Y = Yt + yy, Z = Zt + 4 * zq;
-    const bool store_ok = (Y < g.Y1) && (Z < g.Z1);
-    const int own = (yy + 2) * T::HP + 4 + 4 * zq;  // own column inside a halo slot (floats)
-    const int ctr = yy * TZ + 4 * zq;               // own column inside a centre slot
+    const int Y = Yt + yr * RY, Z = Zt + 4 * zq;       // first of this thread's RY rows
+    const bool z_ok = Z < g.Z1;
+    const int own = (yr * RY + 2) * T::HP + 4 + 4 * zq;  // own column inside a halo slot (floats)
+    const int ctr = yr * RY * TZ + 4 * zq;               // own column inside a centre slot
     constexpr int HSLOT_F = T::HSLOT / 4;
 
     const SourceView &sv = a.s.sv;
     bool chunk_has_src = false;
     if (sv.ncells > 0) chunk_has_src = (sv.plane_off[Xb] - sv.plane_off[Xa]) > 0;
 
-    // prologue: own-column values of planes Xa-2 .. Xa+1 (stages 0..3) into the register queue
-    float4 qm2, qm1, qc, qp1;
-    mbar_wait(full0 + 0, 0);
-    qm2 = lds128(sH + 0 * HSLOT_F + own);
-    mbar_wait(full0 + 8, 0);
-    qm1 = lds128(sH + 1 * HSLOT_F + own);
-    __syncwarp();
-    if (lane == 0) {  // stages 0 and 1 are never a centre plane: release them now
-        mbar_arrive(empty0 + 0);
-        mbar_arrive(empty0 + 8);
+    // Register queue: q[s % 5][r] = this thread's float4 of u[t0] plane (stage s), row r.  All indices are
+    // compile-time constants because the plane loop is unrolled by the ring period.
+    float4 q[5][RY];
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {  // prologue: planes Xa-2 .. Xa+1
+        mbar_wait(full0 + 8 * s, 0);
+#pragma unroll
+        for (int r = 0; r < RY; ++r) q[s][r] = lds128(sH + s * HSLOT_F + own + r * T::HP);
+        if (s == 1) {  // stages 0 and 1 are never a centre plane: release them now
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(empty0 + 0);
+                mbar_arrive(empty0 + 8);
+            }
+        }
     }
-    mbar_wait(full0 + 16, 0);
-    qc = lds128(sH + 2 * HSLOT_F + own);
-    mbar_wait(full0 + 24, 0);
-    qp1 = lds128(sH + 3 * HSLOT_F + own);
 
-    int fs = 4 % S0, fpar = (4 / S0) & 1;  // front stage j+4: slot and phase parity
-    int cs = 2;                            // centre stage j+2: slot
-    int ms = 0;                            // centre-ring slot j % S1
+    int ms = 0;  // centre-ring slot j % S1
     float *__restrict__ out = a.s.u + (long long)a.s.t2 * g.lvl + ((long long)Xa * g.nyp + Y) * g.nzp + Z;
     const long long plane = (long long)g.nyp * g.nzp;
 
-    for (int j = 0; j < np; ++j) {
-        mbar_wait(full0 + 8 * fs, fpar);
-        const float4 qp2 = lds128(sH + fs * HSLOT_F + own);
-        const float4 u1v = lds128(sU1 + ms * (TY * TZ) + ctr);
-        const float4 mv = lds128(sM + ms * (TY * TZ) + ctr);
-        const float *P = sH + cs * HSLOT_F + own;
-        const float4 ym2 = lds128(P - 2 * T::HP), ym1 = lds128(P - T::HP);
-        const float4 yp1 = lds128(P + T::HP), yp2 = lds128(P + 2 * T::HP);
-        const float2 zl = lds64(P - 2), zr = lds64(P + 4);
+    for (int j0 = 0; j0 < np; j0 += S0) {
+        const uint32_t par = (uint32_t)(j0 / S0) & 1u;
+#pragma unroll
+        for (int k = 0; k < S0; ++k) {
+            const int j = j0 + k;
+            if (j >= np) break;
+            const int fsl = (k + 4) % S0, csl = (k + 2) % S0;  // front (stage j+4) and centre (stage j+2) slots
+            mbar_wait(full0 + 8 * fsl, par ^ (uint32_t)((k + 4) / S0));
+            float4 u1v[RY], mv[RY];
+            float2 zl[RY], zr[RY];
+            const float *F = sH + fsl * HSLOT_F + own;
+            const float *P = sH + csl * HSLOT_F + own;
+#pragma unroll
+            for (int r = 0; r < RY; ++r) {
+                q[(k + 4) % 5][r] = lds128(F + r * T::HP);
+                u1v[r] = lds128(sU1 + ms * (TY * TZ) + ctr + r * TZ);
+                mv[r] = lds128(sM + ms * (TY * TZ) + ctr + r * TZ);
+                zl[r] = lds64(P + r * T::HP - 2);
+                zr[r] = lds64(P + r * T::HP + 4);
+            }
+            // the y column of this thread on the centre plane: 2 rows below, own rows (from the queue), 2 above
+            float4 col[RY + 4];
+            col[0] = lds128(P - 2 * T::HP);
+            col[1] = lds128(P - T::HP);
+            col[RY + 2] = lds128(P + RY * T::HP);
+            col[RY + 3] = lds128(P + (RY + 1) * T::HP);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty0 + 8 * csl);  // stage j+2 (and centre slot j % S1) free
+#pragma unroll
+            for (int r = 0; r < RY; ++r) col[r + 2] = q[(k + 2) % 5][r];
 
-        float4 o;
-        o.x = point<EXACT>(qc.x, qm2.x, qm1.x, qp1.x, qp2.x, ym2.x, ym1.x, yp1.x, yp2.x, zl.x, zl.y, qc.y, qc.z, u1v.x, mv.x, a.s.k);
-        o.y = point<EXACT>(qc.y, qm2.y, qm1.y, qp1.y, qp2.y, ym2.y, ym1.y, yp1.y, yp2.y, zl.y, qc.x, qc.z, qc.w, u1v.y, mv.y, a.s.k);
-        o.z = point<EXACT>(qc.z, qm2.z, qm1.z, qp1.z, qp2.z, ym2.z, ym1.z, yp1.z, yp2.z, qc.x, qc.y, qc.w, zr.x, u1v.z, mv.z, a.s.k);
-        o.w = point<EXACT>(qc.w, qm2.w, qm1.w, qp1.w, qp2.w, ym2.w, ym1.w, yp1.w, yp2.w, qc.y, qc.z, zr.x, zr.y, u1v.w, mv.w, a.s.k);
+            float4 o[RY];
+#pragma unroll
+            for (int r = 0; r < RY; ++r) {
+                const float4 c = col[r + 2];
+                const float4 xm2 = q[k % 5][r], xm1 = q[(k + 1) % 5][r], xp1 = q[(k + 3) % 5][r], xp2 = q[(k + 4) % 5][r];
+                const float4 ym2 = col[r], ym1 = col[r + 1], yp1 = col[r + 3], yp2 = col[r + 4];
+                o[r].x = point<EXACT>(c.x, xm2.x, xm1.x, xp1.x, xp2.x, ym2.x, ym1.x, yp1.x, yp2.x, zl[r].x, zl[r].y, c.y, c.z, u1v[r].x, mv[r].x, a.s.k);
+                o[r].y = point<EXACT>(c.y, xm2.y, xm1.y, xp1.y, xp2.y, ym2.y, ym1.y, yp1.y, yp2.y, zl[r].y, c.x, c.z, c.w, u1v[r].y, mv[r].y, a.s.k);
+                o[r].z = point<EXACT>(c.z, xm2.z, xm1.z, xp1.z, xp2.z, ym2.z, ym1.z, yp1.z, yp2.z, c.x, c.y, c.w, zr[r].x, u1v[r].z, mv[r].z, a.s.k);
+                o[r].w = point<EXACT>(c.w, xm2.w, xm1.w, xp1.w, xp2.w, ym2.w, ym1.w, yp1.w, yp2.w, c.y, c.z, zr[r].x, zr[r].y, u1v[r].w, mv[r].w, a.s.k);
+            }
 
-        __syncwarp();
-        if (lane == 0) mbar_arrive(empty0 + 8 * cs);  // stage j+2 (and centre slot j%S1) free
-
-        if (chunk_has_src) {  // fused Section1: rare path, only chunks that contain a source cell
-            const int X = Xa + j;
-            const int c0 = sv.plane_off[X], c1 = sv.plane_off[X + 1];
-            for (int i = c0; i < c1; ++i) {
-                const SourceCell cell = sv.cells[i];
-                const int dzc = cell.Z - Z;
-                if (cell.Y == Y && dzc >= 0 && dzc < 4) {
-                    if (dzc == 0) o.x = apply_cell(o.x, cell, sv);
-                    else if (dzc == 1) o.y = apply_cell(o.y, cell, sv);
-                    else if (dzc == 2) o.z = apply_cell(o.z, cell, sv);
-                    else o.w = apply_cell(o.w, cell, sv);
+            if (chunk_has_src) {  // fused Section1: rare path, only chunks that contain a source cell
+                const int X = Xa + j;
+                const int c0 = sv.plane_off[X], c1 = sv.plane_off[X + 1];
+                for (int i = c0; i < c1; ++i) {
+                    const SourceCell cell = sv.cells[i];
+                    const int dyc = cell.Y - Y, dzc = cell.Z - Z;
+                    if (dyc >= 0 && dyc < RY && dzc >= 0 && dzc < 4) {
+                        // extract / re-insert with selects so o[] stays in registers
+                        float v = 0.f;
+#pragma unroll
+                        for (int r = 0; r < RY; ++r) {
+                            const float e = dzc == 0 ? o[r].x : dzc == 1 ? o[r].y : dzc == 2 ? o[r].z : o[r].w;
+                            v = dyc == r ? e : v;
+                        }
+                        v = apply_cell(v, cell, sv);
+#pragma unroll
+                        for (int r = 0; r < RY; ++r) {
+                            const bool hit = dyc == r;
+                            o[r].x = (hit && dzc == 0) ? v : o[r].x;
+                            o[r].y = (hit && dzc == 1) ? v : o[r].y;
+                            o[r].z = (hit && dzc == 2) ? v : o[r].z;
+                            o[r].w = (hit && dzc == 3) ? v : o[r].w;
+                        }
+                    }
                 }
             }
+#pragma unroll
+            for (int r = 0; r < RY; ++r)
+                if (z_ok && Y + r < g.Y1) *reinterpret_cast<float4 *>(out + (long long)r * g.nzp) = o[r];
+            out += plane;
+            if (++ms == S1) ms = 0;
         }
-        if (store_ok) *reinterpret_cast<float4 *>(out) = o;
-        out += plane;
-
-        qm2 = qm1; qm1 = qc; qc = qp1; qp1 = qp2;
-        if (++fs == S0) { fs = 0; fpar ^= 1; }
-        if (++cs == S0) cs = 0;
-        if (++ms == T::S1) ms = 0;
     }
 }
 
 // ---------------------------------------------------------------------------- host side
 typedef void (*TmaKernelFn)(const TmaArgs);
 struct Variant {
-    int ty, tz, stages;
+    int ty, tz, rows, stages;
     bool exact;
     TmaKernelFn fn;
     int nt;
@@ -257,21 +318,24 @@ struct Variant {
     int minb;
 };
 
-#define FDTD_VARIANT(TY_, TZ_, S_, MINB_)                                                                   \
-    {TY_, TZ_, S_, true, stencil_tma_kernel<TY_, TZ_, S_, true, MINB_>, TileShape<TY_, TZ_, S_>::NT,         \
-     (size_t)TileShape<TY_, TZ_, S_>::SMEM, MINB_},                                                          \
-    {TY_, TZ_, S_, false, stencil_tma_kernel<TY_, TZ_, S_, false, MINB_>, TileShape<TY_, TZ_, S_>::NT,       \
-     (size_t)TileShape<TY_, TZ_, S_>::SMEM, MINB_}
+#define FDTD_V1(TY_, TZ_, RY_, NS_, EX_, MINB_)                                                             \
+    {TY_, TZ_, RY_, NS_, EX_, stencil_tma_kernel<TY_, TZ_, RY_, NS_, EX_, MINB_>,                           \
+     TileShape<TY_, TZ_, RY_, NS_>::NT, (size_t)TileShape<TY_, TZ_, RY_, NS_>::SMEM, MINB_}
+#define FDTD_VARIANT(TY_, TZ_, RY_, MINB_) FDTD_V1(TY_, TZ_, RY_, 5, true, MINB_), FDTD_V1(TY_, TZ_, RY_, 5, false, MINB_)
 
 static const Variant g_variants[] = {
-    // (TY, TZ, stages, min CTAs/SM).  MINB is chosen so the register cap stays >= 72 (no spills):
-    // the steady-state loop keeps a 4-plane float4 queue + 6 neighbour vectors live.
-    // For each tile the preferred stage count comes first (auto selection takes the first match).
-    FDTD_VARIANT(16, 64, 6, 3),  FDTD_VARIANT(16, 64, 5, 2),  FDTD_VARIANT(32, 64, 6, 1),
-    FDTD_VARIANT(32, 64, 8, 1),  FDTD_VARIANT(16, 128, 6, 1), FDTD_VARIANT(16, 128, 8, 1),
-    FDTD_VARIANT(8, 128, 6, 3),  FDTD_VARIANT(8, 128, 5, 2),  FDTD_VARIANT(8, 64, 6, 5),
-    FDTD_VARIANT(8, 64, 5, 4),   FDTD_VARIANT(16, 32, 6, 5),  FDTD_VARIANT(16, 32, 5, 4),
-    FDTD_VARIANT(8, 32, 6, 8),   FDTD_VARIANT(32, 32, 6, 3),
+    // (TY, TZ, rows per thread, min CTAs/SM), ring depth 5, both arithmetic modes.  Auto selection takes
+    // the first match, so the preferred row count of a tile comes first.
+    FDTD_VARIANT(8, 64, 2, 4),   FDTD_VARIANT(8, 64, 1, 4),   FDTD_VARIANT(8, 128, 1, 2),
+    FDTD_VARIANT(8, 128, 2, 3),  FDTD_VARIANT(16, 64, 2, 3),  FDTD_VARIANT(16, 64, 1, 2),
+    FDTD_VARIANT(16, 128, 2, 2), FDTD_VARIANT(16, 128, 1, 1), FDTD_VARIANT(32, 64, 2, 2),
+    FDTD_VARIANT(32, 64, 1, 1),  FDTD_VARIANT(16, 32, 2, 4),  FDTD_VARIANT(16, 32, 1, 4),
+    FDTD_VARIANT(8, 32, 1, 6),   FDTD_VARIANT(32, 32, 2, 3),  FDTD_VARIANT(32, 128, 2, 1),
+    FDTD_VARIANT(32, 64, 4, 1),  FDTD_VARIANT(32, 128, 4, 1), FDTD_VARIANT(14, 64, 1, 2),
+    FDTD_VARIANT(14, 128, 1, 1), FDTD_VARIANT(28, 64, 2, 2),
+    // deeper prefetch (ring depth 10), contracted arithmetic only (the exact loop body is too large to unroll x10)
+    FDTD_V1(8, 64, 2, 10, false, 3),  FDTD_V1(8, 128, 2, 10, false, 2), FDTD_V1(16, 64, 2, 10, false, 2),
+    FDTD_V1(8, 64, 1, 10, false, 3),  FDTD_V1(16, 128, 2, 10, false, 1),
 };
 static const int g_nvariants = (int)(sizeof(g_variants) / sizeof(g_variants[0]));
 
@@ -317,18 +381,21 @@ int tma_plan_build(TmaPlan &p, float *u, const float *m, const Grid &g, const Tm
     if (!tma_supported(g)) return (int)cudaErrorInvalidValue;
     const int ny = g.Y1 - g.Y0, nz = g.Z1 - g.Z0, nx = g.X1 - g.X0;
 
-    // ---- tile choice: explicit, or the auto heuristic (largest z tile that the row fills, then the
-    // y tile / stage count with the most bytes in flight that still gives >= 2 CTAs per SM).
-    int ty = cfg.ty, tz = cfg.tz;
-    if (tz <= 0) tz = nz >= 64 ? 64 : 32;
-    if (ty <= 0) ty = ny >= 16 ? 16 : 8;
+    // ---- tile choice: explicit, or the measured optimum of the 512^3 sweep (profiles/r01_sweep512.txt):
+    // small y tiles keep many CTAs per SM in flight; the exact path is issue-bound and wants one row per
+    // thread (92 registers), the contracted path is bandwidth-bound and wants two rows of a 128-wide tile.
+    int ty = cfg.ty, tz = cfg.tz, rows = cfg.rows;
+    if (tz <= 0) tz = exact ? (nz >= 64 ? 64 : 32) : (nz >= 128 ? 128 : (nz >= 64 ? 64 : 32));
+    if (ty <= 0) ty = 8;
+    if (rows <= 0) rows = (exact || tz == 32) ? 1 : 2;
     int vi = -1;
-    for (int i = 0; i < g_nvariants && vi < 0; ++i)
-        if (g_variants[i].ty == ty && g_variants[i].tz == tz && g_variants[i].exact == exact &&
-            (cfg.stages <= 0 || g_variants[i].stages == cfg.stages))
-            vi = i;
+    for (int pass = 0; pass < 2 && vi < 0; ++pass)  // pass 1: any row count, if the caller did not ask for one
+        for (int i = 0; i < g_nvariants && vi < 0; ++i)
+            if (g_variants[i].ty == ty && g_variants[i].tz == tz && g_variants[i].exact == exact &&
+                (g_variants[i].rows == rows || (pass == 1 && cfg.rows <= 0)) &&
+                (cfg.stages <= 0 ? g_variants[i].stages == 5 : g_variants[i].stages == cfg.stages))
+                vi = i;
     if (vi < 0) return (int)cudaErrorInvalidValue;
-    const int stages = g_variants[vi].stages;
     const Variant &v = g_variants[vi];
 
     cuuint64_t dims_u[4] = {(cuuint64_t)g.nzp, (cuuint64_t)g.nyp, (cuuint64_t)g.nxp, 3};
@@ -346,20 +413,35 @@ int tma_plan_build(TmaPlan &p, float *u, const float *m, const Grid &g, const Tm
     if (e != cudaSuccess) return (int)e;
     if (occ < 1) return (int)cudaErrorInvalidConfiguration;
 
-    // ---- x chunking: enough CTAs to fill every SM `occ` deep in one wave, no more.
+    // ---- x chunking.  CTAs = tiles x chunks are dispatched in waves of `slots` = SMs x resident CTAs.
+    // Several waves let the hardware scheduler even out the SMs (one wave leaves the issue-bound exact path
+    // at 85% of roofline, ~7 reach 97%), but a partially filled last wave idles the machine and every chunk
+    // re-reads 4 pipeline-prologue planes of u[t0] (a quarter of the traffic).  Score each chunk count by
+    // wave efficiency / prologue overhead and keep the best.
     const int tiles = ((ny + ty - 1) / ty) * ((nz + tz - 1) / tz);
     int xchunk = cfg.xchunk;
     if (xchunk <= 0) {
-        const int slots = sm_count * occ;
-        int nchunks = slots / tiles;
-        if (nchunks < 1) nchunks = 1;
-        if (nchunks > nx) nchunks = nx;
-        xchunk = (nx + nchunks - 1) / nchunks;
-        if (xchunk < 8 && nx >= 8) xchunk = 8;
+        const double slots = (double)sm_count * occ;
+        double best = -1.0;
+        for (int nch = 1; nch <= nx; ++nch) {
+            const int xc = (nx + nch - 1) / nch;
+            if (xc < 8 && nch > 1) break;
+            if ((nx + xc - 1) / xc != nch) continue;  // not a distinct chunking
+            const double waves = tiles * (double)nch / slots;
+            const double full = ceil(waves);
+            double eff = waves / full;                       // last-wave quantisation
+            eff *= full / (full + 0.35);                     // ramp-up/drain of the launch amortised over the waves
+            eff /= 1.0 + 0.25 * 4.0 / xc + 1.5 / (xc + 4.0); // prologue re-reads + pipeline fill latency
+            if (eff > best) {
+                best = eff;
+                xchunk = xc;
+            }
+        }
     }
     p.ty = ty;
     p.tz = tz;
-    p.stages = stages;
+    p.rows = v.rows;
+    p.stages = v.stages;
     p.xchunk = xchunk;
     p.variant = vi;
     p.smem_bytes = v.smem;

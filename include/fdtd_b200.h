@@ -133,7 +133,7 @@ double fdtd_b200_plan_last_kernel_seconds(fdtd_b200_plan *plan);
 /*
  * Options: "kernel" 0 = auto, 1 = generic (any extents), 2 = tma (2.5D x-streaming, TMA ring);
  * "exact" 1 = replay the reference's fp32 operation order (0 ulp vs the host build), 0 = contracted;
- * "fuse_inject" 1 = scatter inside the stencil epilogue; "tile_y","tile_z","stages","xchunk";
+ * "fuse_inject" 1 = scatter inside the stencil epilogue; "tile_y","tile_z","rows","xchunk";
  * "graph" 1 = replay the time loop as a CUDA graph; "t_fuse" temporal-blocking depth.
  */
 int fdtd_b200_plan_set_option(fdtd_b200_plan *plan, const char *key, int value);

@@ -106,22 +106,27 @@ def random_case(rng, shape, T, S):
     return u, m, src, crd
 
 
-TILES = [(32, 64, 6), (32, 64, 8), (16, 64, 5), (16, 64, 6), (16, 128, 6), (16, 128, 8), (8, 128, 5), (8, 128, 6),
-         (8, 64, 5), (8, 64, 6), (16, 32, 5), (16, 32, 6), (8, 32, 6), (32, 32, 6)]
+TILES = [(32, 64, 2), (32, 64, 1), (16, 64, 2), (16, 64, 1), (16, 128, 2), (16, 128, 1), (8, 128, 2), (8, 128, 1),
+         (8, 64, 2), (8, 64, 1), (16, 32, 2), (16, 32, 1), (8, 32, 1), (32, 32, 2), (32, 128, 2), (32, 64, 4),
+         (32, 128, 4), (14, 64, 1), (14, 128, 1), (28, 64, 2)]
 
 
-@pytest.mark.parametrize("ty,tz,stages", TILES)
-def test_tma_variants_bit_exact(pkg, oracle, ty, tz, stages):
+@pytest.mark.parametrize("ty,tz,rows", TILES)
+def test_tma_variants_bit_exact(pkg, oracle, ty, tz, rows):
     """Every tile instantiation, on a grid that is NOT a multiple of the tile (ragged edges in y and z),
     several x chunks, random m, sources inside / on the boundary / outside."""
-    rng = np.random.default_rng(100 + ty + tz + stages)
+    rng = np.random.default_rng(100 + ty + tz + rows)
     shape = (21, 44, 72)
     u, m, src, crd = random_case(rng, shape, 8, 6)
-    ref = u.copy()
+    ref, ref0 = u.copy(), u.copy()
     oracle.run(ref, m, src, crd, impl="port")
-    t, info = run_plan(pkg, u, m, src, crd, options={"kernel": 2, "tile_y": ty, "tile_z": tz, "stages": stages, "xchunk": 8})
+    t, info = run_plan(pkg, u, m, src, crd, options={"kernel": 2, "tile_y": ty, "tile_z": tz, "rows": rows, "xchunk": 8})
     assert info["kernel_used"] == 2 and (info["tile_y_used"], info["tile_z_used"]) == (ty, tz)
     assert bits_equal(u, ref)
+    # same variant, contracted arithmetic: within the reference's tolerance
+    v = ref0.copy()
+    run_plan(pkg, v, m, src, crd, options={"kernel": 2, "tile_y": ty, "tile_z": tz, "rows": rows, "exact": 0})
+    assert oracle.rel_l2(v, ref) < REL_L2_TOL
 
 
 @pytest.mark.parametrize("kernel", [1, 2])
@@ -234,7 +239,11 @@ def test_512_properties(pkg, oracle, golden):
         p.run(0, T - 1)
         u2 = p.download()
     assert t.section0 > 0
-    assert bits_equal(u2, 2 * u)
+    # doubling the source doubles the field; exact in binary fp except for roundings in the denormal range
+    # (a third of this wavefield is denormal), which perturb the last bits of their neighbours
+    assert np.allclose(u2, 2 * u, rtol=1e-4, atol=1e-37)
+    big = np.abs(u) > 1e-12
+    assert big.sum() > 1000 and bits_equal(u2[big], 2 * u[big])
     # window: the source sits at cell 127.75 and the support radius after 50 steps is < 30 cells, so a
     # 160^3 oracle run with the SAME physical coordinates (same pos/frac bits) reproduces the low corner
     w = 160

@@ -13,23 +13,30 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 pkg = importlib.import_module("accelerated-3d-acoustic-fdtd-kernel_b200")
 
-TILES = [(16, 64, 6), (16, 64, 5), (32, 64, 6), (32, 64, 8), (16, 128, 6), (16, 128, 8), (8, 128, 6), (8, 128, 5),
-         (8, 64, 6), (8, 64, 5), (16, 32, 6), (16, 32, 5), (8, 32, 6), (32, 32, 6)]
+TILES = [(8, 64, 2, 5), (8, 64, 1, 5), (8, 128, 1, 5), (8, 128, 2, 5), (16, 64, 2, 5), (16, 64, 1, 5), (16, 128, 2, 5),
+         (16, 128, 1, 5), (32, 64, 2, 5), (32, 64, 1, 5), (16, 32, 2, 5), (16, 32, 1, 5), (8, 32, 1, 5), (32, 32, 2, 5),
+         (32, 128, 2, 5), (32, 64, 4, 5), (32, 128, 4, 5), (14, 64, 1, 5), (14, 128, 1, 5), (28, 64, 2, 5),
+         (8, 64, 2, 10), (8, 128, 2, 10), (16, 64, 2, 10), (8, 64, 1, 10), (16, 128, 2, 10)]
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--n", type=int, default=512)
     ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--shape", type=str, default="", help="nx,ny,nz (overrides --n)")
     ap.add_argument("--xchunks", type=str, default="0")
     ap.add_argument("--exact", type=str, default="1,0")
     ap.add_argument("--tiles", type=str, default="")
     ap.add_argument("--generic", action="store_true")
+    ap.add_argument("--dense", action="store_true", help="dense sin field instead of the zero field")
     a = ap.parse_args()
     n, T = a.n, a.steps + 5
+    nx, ny, nz = [int(x) for x in a.shape.split(",")] if a.shape else (n, n, n)
+    npts = nx * ny * nz
     tiles = TILES if not a.tiles else [tuple(int(x) for x in t.split("x")) for t in a.tiles.split(",")]
-    src, crd = pkg.fill_ricker(T, 1), pkg.fill_source_coords(1, n, n, n)
-    with pkg.Plan(n, n, n, deviceid=0) as p:
+    tiles = [t if len(t) == 4 else t + (5,) for t in tiles]
+    src, crd = pkg.fill_ricker(T, 1), pkg.fill_source_coords(1, nx, ny, nz)
+    with pkg.Plan(nx, ny, nz, deviceid=0) as p:
         p.set_sources(src, crd)
         rows = []
         if a.generic:
@@ -38,21 +45,22 @@ def main():
                 p.set_option("kernel", 1)
                 p.set_option("exact", exact)
                 t = p.run(0, T - 1)
-                g = n ** 3 * a.steps / (t.section0 + t.section1) / 1e9
+                g = npts * a.steps / (t.section0 + t.section1) / 1e9
                 print(f"generic exact={exact}: {g:8.1f} Gpts/s  {16 * g / 6551.7:6.3f} of HBM", flush=True)
-        for (ty, tz, st), xc, exact in itertools.product(tiles, [int(x) for x in a.xchunks.split(",")],
+        for (ty, tz, st, ns), xc, exact in itertools.product(tiles, [int(x) for x in a.xchunks.split(",")],
                                                           [int(x) for x in a.exact.split(",")]):
-            p.fill(0.0, 1.5)
-            for k, v in (("kernel", 2), ("exact", exact), ("tile_y", ty), ("tile_z", tz), ("stages", st), ("xchunk", xc)):
+            p.fill_dense() if a.dense else p.fill(0.0, 1.5)
+            for k, v in (("kernel", 2), ("exact", exact), ("tile_y", ty), ("tile_z", tz), ("rows", st), ("stages", ns),
+                         ("xchunk", xc)):
                 p.set_option(k, v)
             try:
                 t = p.run(0, T - 1)
             except pkg.FdtdError as e:
-                print(f"tile {ty}x{tz} s{st} xc{xc} exact={exact}: {e}", flush=True)
+                print(f"tile {ty}x{tz} r{st} s{ns} xc{xc} exact={exact}: {e}", flush=True)
                 continue
-            g = n ** 3 * a.steps / (t.section0 + t.section1) / 1e9
-            rows.append((g, ty, tz, st, p.get_option("xchunk_used"), exact))
-            print(f"tile {ty:3d}x{tz:3d} s{st} xchunk {rows[-1][4]:4d} exact={exact}: {g:8.1f} Gpts/s  "
+            g = npts * a.steps / (t.section0 + t.section1) / 1e9
+            rows.append((g, ty, tz, st, ns, p.get_option("xchunk_used"), exact))
+            print(f"tile {ty:3d}x{tz:3d} r{st} s{ns:2d} xchunk {rows[-1][5]:4d} exact={exact}: {g:8.1f} Gpts/s  "
                   f"{16 * g / 6551.7:6.3f} of HBM  ({p.last_kernel_seconds * 1e6:8.1f} us/step)", flush=True)
     rows.sort(reverse=True)
     print("best:", rows[:5])

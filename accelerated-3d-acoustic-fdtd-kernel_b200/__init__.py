@@ -23,6 +23,10 @@ from .host import (  # noqa: F401
     fill_source_coords,
     lib,
     lib_path,
+    run_slabs,
+    slab_source_cells,
     source_table,
     write_benchmark_csv,
 )
+from . import slab  # noqa: E402,F401
+from .slab import LocalSlabs, SlabRun, partition  # noqa: E402,F401

@@ -45,6 +45,24 @@ struct SourceView {
     int ncells;
 };
 
+// Neighbours of this slab along x (side 0 = lower planes, side 1 = upper planes).  The stencil kernel
+// stores its two boundary planes straight into the neighbour's ghost planes through a peer-mapped
+// pointer (NVLink) and, when the last CTA touching that boundary is done, raises the neighbour's
+// ready flag with the step's epoch; the next step's producer threads wait on their own flags before
+// loading ghost planes.  No separate exchange kernel, copy or collective exists.
+struct SlabLink {
+    float *peer_u[2];        // neighbour's u base (peer-mapped); nullptr = physical boundary
+    long long peer_lvl[2];   // neighbour's elements per level
+    int peer_plane[2];       // first ghost plane to fill in the neighbour (its X1, resp. its X0-2)
+    int *peer_flag[2];       // flag in the neighbour's memory that THIS slab raises
+    int *my_flag[2];         // flags in this slab's memory raised by the neighbours
+    int *counter;            // [2] CTAs of this launch that finished each boundary
+    int *err;                // set to 1 if a flag wait timed out
+    int expect[2];           // CTAs touching each boundary in this launch
+    int epoch;               // sequence number of this step (same on every slab)
+    int wait;                // 1: ghost planes of u[t0] were produced by the neighbours' step epoch-1
+};
+
 // Field geometry of one slab as the kernels see it.
 struct Grid {
     int nxp, nyp, nzp;       // padded extents

@@ -12,6 +12,7 @@ struct StepArgs {
     Coef k;
     int t0, t1, t2;    // ring: current, previous, next
     SourceView sv;     // sv.ncells == 0 -> no fused injection
+    SlabLink link;     // x-slab neighbours (all null for a single slab)
 };
 
 // --- generic kernel: any extents / alignment, one point per thread, loads through L1/L2.

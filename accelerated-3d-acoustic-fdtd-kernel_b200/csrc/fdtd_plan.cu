@@ -21,6 +21,9 @@
 
 using namespace fdtd;
 
+static void shape_from_geometry(const fdtd_b200_geometry *geo, PlanShape &s);
+static void grid_from_shape(const PlanShape &s, Grid &g);
+
 // ---------------------------------------------------------------------------- runtime config
 static int g_use_tc = 0, g_t_fuse = 1, g_nfields = 1;
 
@@ -99,16 +102,7 @@ int fdtd::plan_create_internal(const PlanShape &s, fdtd_b200_plan **out)
     p->shape = s;
     FDTD_CHECK(cudaGetDevice(&p->dev));
     cudaDeviceGetAttribute(&p->sm_count, cudaDevAttrMultiProcessorCount, p->dev);
-    p->g.nxp = s.nxp;
-    p->g.nyp = s.nyp;
-    p->g.nzp = s.nzp;
-    p->g.X0 = s.x_m + FDTD_HALO;
-    p->g.X1 = s.x_M + FDTD_HALO + 1;
-    p->g.Y0 = s.y_m + FDTD_HALO;
-    p->g.Y1 = s.y_M + FDTD_HALO + 1;
-    p->g.Z0 = s.z_m + FDTD_HALO;
-    p->g.Z1 = s.z_M + FDTD_HALO + 1;
-    p->g.lvl = (long long)s.nxp * s.nyp * s.nzp;
+    grid_from_shape(s, p->g);
     // openacc.cpp:84-87, fp32 on the host
     p->k.dt2 = s.dt * s.dt;
     p->k.r1 = 1.0F / (s.dt * s.dt);
@@ -136,7 +130,16 @@ int fdtd::plan_create_internal(const PlanShape &s, fdtd_b200_plan **out)
     p->opt_t_fuse = g_t_fuse;
 
     cudaError_t e = cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaMalloc(&p->d_u, 3 * (size_t)p->g.lvl * sizeof(float));
+    p->flags_offset = (3 * (size_t)p->g.lvl * sizeof(float) + 255) / 256 * 256;
+    if (e == cudaSuccess) e = cudaMalloc(&p->d_u, p->flags_offset + 256);
+    if (e == cudaSuccess) {
+        p->d_flags = reinterpret_cast<int *>(reinterpret_cast<char *>(p->d_u) + p->flags_offset);
+        e = cudaMemset(p->d_flags, 0, 256);
+        p->link.my_flag[0] = p->d_flags + 0;
+        p->link.my_flag[1] = p->d_flags + 1;
+        p->link.counter = p->d_flags + 2;
+        p->link.err = p->d_flags + 4;
+    }
     if (e == cudaSuccess) e = cudaMalloc(&p->d_m, (size_t)p->g.lvl * sizeof(float));
     if (e != cudaSuccess) {
         fdtd_b200_plan_destroy(p);
@@ -149,28 +152,9 @@ int fdtd::plan_create_internal(const PlanShape &s, fdtd_b200_plan **out)
 extern "C" int fdtd_b200_plan_create(const fdtd_b200_geometry *geo, fdtd_b200_plan **out)
 {
     if (!geo || geo->nx < 1 || geo->ny < 1 || geo->nz < 1) return (int)cudaErrorInvalidValue;
-    PlanShape s{};
-    s.nxp = geo->nx + 2 * FDTD_HALO;
-    s.nyp = geo->ny + 2 * FDTD_HALO;
-    s.nzp = geo->nz + 2 * FDTD_HALO;
-    s.x_m = 0;
-    s.x_M = geo->nx - 1;
-    s.y_m = 0;
-    s.y_M = geo->ny - 1;
-    s.z_m = 0;
-    s.z_M = geo->nz - 1;
-    s.dt = geo->dt;
-    s.h_x = geo->h_x;
-    s.h_y = geo->h_y;
-    s.h_z = geo->h_z;
-    s.o_x = geo->o_x;
-    s.o_y = geo->o_y;
-    s.o_z = geo->o_z;
-    s.x_offset = geo->x_offset;
-    s.gx_m = 0;
-    s.gx_M = (geo->nx_global > 0 ? geo->nx_global : geo->nx) - 1;
+    PlanShape s;
+    shape_from_geometry(geo, s);
     if (s.x_offset < 0 || s.x_offset + geo->nx - 1 > s.gx_M) return (int)cudaErrorInvalidValue;
-    s.deviceid = geo->deviceid;
     return plan_create_internal(s, out);
 }
 
@@ -179,9 +163,11 @@ extern "C" int fdtd_b200_plan_destroy(fdtd_b200_plan *p)
     if (!p) return 0;
     cudaSetDevice(p->dev);
     plan_free_sources(p);
+    for (int s = 0; s < 2; ++s)
+        if (p->ipc_base[s]) cudaIpcCloseMemHandle(p->ipc_base[s]);
     cudaFree(p->d_u);
     cudaFree(p->d_m);
-    if (p->stream) cudaStreamDestroy(p->stream);
+    if (p->stream && p->owns_stream) cudaStreamDestroy(p->stream);
     delete p;
     return 0;
 }
@@ -233,24 +219,26 @@ extern "C" int fdtd_b200_plan_fill_dense(fdtd_b200_plan *p)
 }
 
 // ---------------------------------------------------------------------------- sources
-extern "C" int fdtd_b200_plan_set_sources(fdtd_b200_plan *p, const float *src, int src_size0, int pstride,
-                                          const float *coords, int ncoords, int cstride, int p_src_m, int p_src_M)
-{
-    if (!p) return (int)cudaErrorInvalidValue;
-    FDTD_CHECK(cudaSetDevice(p->dev));
-    plan_free_sources(p);
-    // the reference's guard, openacc.cpp:113
-    if (!(src_size0 * pstride > 0 && p_src_M - p_src_m + 1 > 0) || !src || !coords) return 0;
-    if (p_src_m < 0 || p_src_M >= ncoords || p_src_M >= pstride || cstride < 3) return (int)cudaErrorInvalidValue;
+// Per-cell scatter table of one slab: which cells receive which sources with which weight, in the
+// serial order of openacc.cpp:116-136 (cells sorted by (X,Y,Z), contributions ascending in p_src).
+// Cells inside the Section0 write range come first (they are fused into the stencil epilogue).
+struct SourceTable {
+    std::vector<SourceCell> cells;     // interior cells, then halo cells
+    std::vector<SourceContrib> contribs;
+    std::vector<int> plane_off;        // [nxp+1], interior cells only
+    std::vector<long long> base_idx;   // [p_src_M+1] linear index of each source's base corner, -1 = unused
+    int ncells_int = 0;
+};
 
-    const PlanShape &s = p->shape;
-    const Grid &g = p->g;
+static void build_source_table(const PlanShape &s, const Grid &g, const float *coords, int cstride, int p_src_m,
+                               int p_src_M, SourceTable &t)
+{
     const bool first_slab = s.x_offset + s.x_m == s.gx_m, last_slab = s.x_offset + s.x_M == s.gx_M;
     const int lo[3] = {s.gx_m, s.y_m, s.z_m}, hi[3] = {s.gx_M, s.y_M, s.z_M};
     const float o[3] = {s.o_x, s.o_y, s.o_z}, h[3] = {s.h_x, s.h_y, s.h_z};
 
     std::map<std::tuple<int, int, int>, std::vector<SourceContrib>> cells;  // ordered by (X,Y,Z); p ascending inside
-    std::vector<long long> base_idx((size_t)p_src_M + 1, -1);
+    t.base_idx.assign((size_t)p_src_M + 1, -1);
     for (int ps = p_src_m; ps <= p_src_M; ++ps) {
         int pos[3], in_range[8];
         float frac[3], w[8];
@@ -270,30 +258,116 @@ extern "C" int fdtd_b200_plan_set_sources(fdtd_b200_plan *p, const float *src, i
                     any = true;
                 }
         if (any)
-            base_idx[ps] = ((long long)(pos[0] - s.x_offset + FDTD_HALO) * g.nyp + (pos[1] + FDTD_HALO)) * g.nzp +
-                           (pos[2] + FDTD_HALO);
+            t.base_idx[ps] = ((long long)(pos[0] - s.x_offset + FDTD_HALO) * g.nyp + (pos[1] + FDTD_HALO)) * g.nzp +
+                             (pos[2] + FDTD_HALO);
     }
-
-    // interior cells first (sorted by plane), then the cells outside the Section0 write range ("halo" cells)
     std::vector<SourceCell> cint, chalo;
-    std::vector<SourceContrib> contribs;
     for (auto &kv : cells) {
         SourceCell c;
         std::tie(c.X, c.Y, c.Z) = kv.first;
-        c.first = (int)contribs.size();
+        c.first = (int)t.contribs.size();
         c.count = (int)kv.second.size();
-        contribs.insert(contribs.end(), kv.second.begin(), kv.second.end());
+        t.contribs.insert(t.contribs.end(), kv.second.begin(), kv.second.end());
         const bool interior = c.X >= g.X0 && c.X < g.X1 && c.Y >= g.Y0 && c.Y < g.Y1 && c.Z >= g.Z0 && c.Z < g.Z1;
         (interior ? cint : chalo).push_back(c);
     }
-    std::vector<int> plane_off((size_t)g.nxp + 1, 0);
-    for (const SourceCell &c : cint) plane_off[c.X + 1]++;
-    for (int x = 0; x < g.nxp; ++x) plane_off[x + 1] += plane_off[x];
-    std::vector<SourceCell> all(cint);
-    all.insert(all.end(), chalo.begin(), chalo.end());
+    t.plane_off.assign((size_t)g.nxp + 1, 0);
+    for (const SourceCell &c : cint) t.plane_off[c.X + 1]++;
+    for (int x = 0; x < g.nxp; ++x) t.plane_off[x + 1] += t.plane_off[x];
+    t.ncells_int = (int)cint.size();
+    t.cells = cint;
+    t.cells.insert(t.cells.end(), chalo.begin(), chalo.end());
+}
 
-    p->ncells_int = (int)cint.size();
-    p->ncells_halo = (int)chalo.size();
+static void shape_from_geometry(const fdtd_b200_geometry *geo, PlanShape &s)
+{
+    s = PlanShape{};
+    s.nxp = geo->nx + 2 * FDTD_HALO;
+    s.nyp = geo->ny + 2 * FDTD_HALO;
+    s.nzp = geo->nz + 2 * FDTD_HALO;
+    s.x_m = 0;
+    s.x_M = geo->nx - 1;
+    s.y_m = 0;
+    s.y_M = geo->ny - 1;
+    s.z_m = 0;
+    s.z_M = geo->nz - 1;
+    s.dt = geo->dt;
+    s.h_x = geo->h_x;
+    s.h_y = geo->h_y;
+    s.h_z = geo->h_z;
+    s.o_x = geo->o_x;
+    s.o_y = geo->o_y;
+    s.o_z = geo->o_z;
+    s.x_offset = geo->x_offset;
+    s.gx_m = 0;
+    s.gx_M = (geo->nx_global > 0 ? geo->nx_global : geo->nx) - 1;
+    s.deviceid = geo->deviceid;
+}
+
+static void grid_from_shape(const PlanShape &s, Grid &g)
+{
+    g.nxp = s.nxp;
+    g.nyp = s.nyp;
+    g.nzp = s.nzp;
+    g.X0 = s.x_m + FDTD_HALO;
+    g.X1 = s.x_M + FDTD_HALO + 1;
+    g.Y0 = s.y_m + FDTD_HALO;
+    g.Y1 = s.y_M + FDTD_HALO + 1;
+    g.Z0 = s.z_m + FDTD_HALO;
+    g.Z1 = s.z_M + FDTD_HALO + 1;
+    g.lvl = (long long)s.nxp * s.nyp * s.nzp;
+}
+
+// Host-only view of the table (no GPU): what a slab would scatter.  cells is [max_cells][5] = X,Y,Z,first,count.
+extern "C" int fdtd_b200_slab_source_cells(const fdtd_b200_geometry *geo, const float *coords, int ncoords,
+                                           int cstride, int p_src_m, int p_src_M, int max_cells, int *cells,
+                                           int *ncells_int, int *ncells_all, int max_contribs, int *contrib_p,
+                                           float *contrib_w, int *ncontribs, long long *base_idx)
+{
+    if (!geo || !coords || p_src_m < 0 || p_src_M >= ncoords || cstride < 3) return (int)cudaErrorInvalidValue;
+    PlanShape s;
+    Grid g;
+    shape_from_geometry(geo, s);
+    grid_from_shape(s, g);
+    SourceTable t;
+    build_source_table(s, g, coords, cstride, p_src_m, p_src_M, t);
+    if ((int)t.cells.size() > max_cells || (int)t.contribs.size() > max_contribs) return (int)cudaErrorInvalidValue;
+    for (size_t i = 0; i < t.cells.size(); ++i) {
+        const SourceCell &c = t.cells[i];
+        int *o = cells + 5 * i;
+        o[0] = c.X; o[1] = c.Y; o[2] = c.Z; o[3] = c.first; o[4] = c.count;
+    }
+    for (size_t i = 0; i < t.contribs.size(); ++i) {
+        contrib_p[i] = t.contribs[i].p;
+        contrib_w[i] = t.contribs[i].w;
+    }
+    if (ncells_int) *ncells_int = t.ncells_int;
+    if (ncells_all) *ncells_all = (int)t.cells.size();
+    if (ncontribs) *ncontribs = (int)t.contribs.size();
+    if (base_idx)
+        for (int ps = 0; ps <= p_src_M; ++ps) base_idx[ps] = t.base_idx[ps];
+    return 0;
+}
+
+extern "C" int fdtd_b200_plan_set_sources(fdtd_b200_plan *p, const float *src, int src_size0, int pstride,
+                                          const float *coords, int ncoords, int cstride, int p_src_m, int p_src_M)
+{
+    if (!p) return (int)cudaErrorInvalidValue;
+    FDTD_CHECK(cudaSetDevice(p->dev));
+    plan_free_sources(p);
+    // the reference's guard, openacc.cpp:113
+    if (!(src_size0 * pstride > 0 && p_src_M - p_src_m + 1 > 0) || !src || !coords) return 0;
+    if (p_src_m < 0 || p_src_M >= ncoords || p_src_M >= pstride || cstride < 3) return (int)cudaErrorInvalidValue;
+
+    SourceTable tab;
+    build_source_table(p->shape, p->g, coords, cstride, p_src_m, p_src_M, tab);
+    const std::vector<SourceCell> &all = tab.cells;
+    const std::vector<SourceContrib> &contribs = tab.contribs;
+    const std::vector<int> &plane_off = tab.plane_off;
+    const std::vector<long long> &base_idx = tab.base_idx;
+
+    p->ncells_int = tab.ncells_int;
+    p->ncells_halo = (int)all.size() - tab.ncells_int;
     p->ncells_all = (int)all.size();
     p->src_size0 = src_size0;
     p->pstride = pstride;
@@ -362,7 +436,7 @@ extern "C" int fdtd_b200_plan_get_option(fdtd_b200_plan *p, const char *key, int
 // then the stand-alone scatter for whatever was not fused (halo cells, or everything when fusion is
 // off).  mark(true)/mark(false) are called right before/after a scatter launch (section timers).
 template <class Mark>
-static int plan_step(fdtd_b200_plan *p, int time, Mark &&mark)
+static int plan_step(fdtd_b200_plan *p, int time, bool first_of_run, Mark &&mark)
 {
     const int t0 = ((time % 3) + 3) % 3, t1 = (((time + 2) % 3) + 3) % 3, t2 = (((time + 1) % 3) + 3) % 3;
     const bool has_src = p->ncells_all > 0 && time >= 0 && time < p->src_size0;
@@ -385,6 +459,9 @@ static int plan_step(fdtd_b200_plan *p, int time, Mark &&mark)
         a.sv.mbase = p->d_mbase;
         a.sv.ncells = p->ncells_int;
     }
+    a.link = p->link;
+    a.link.epoch = ++p->epoch;
+    a.link.wait = first_of_run ? 0 : 1;  // the first step's ghost planes come from the caller's initial state
     int rc;
     if (p->kernel_used == 2)
         rc = launch_stencil_tma(p->tma, a, p->opt_exact != 0, p->stream);
@@ -409,16 +486,26 @@ static int plan_step(fdtd_b200_plan *p, int time, Mark &&mark)
     return 0;
 }
 
-extern "C" int fdtd_b200_plan_run(fdtd_b200_plan *p, int time_m, int time_M, struct profiler *timers)
+// Per-slab bookkeeping of one run.
+struct RunState {
+    std::vector<cudaEvent_t> ev;
+    cudaEvent_t e_begin = nullptr, e_end = nullptr;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> s1_spans;  // Section1 = stand-alone scatter launches only
+    cudaEvent_t stamp(cudaStream_t s)
+    {
+        cudaEvent_t e = nullptr;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, s);
+        ev.push_back(e);
+        return e;
+    }
+};
+
+static int plan_prepare(fdtd_b200_plan *p)
 {
-    if (!p) return (int)cudaErrorInvalidValue;
     FDTD_CHECK(cudaSetDevice(p->dev));
-    if (timers) timers->section0 = timers->section1 = 0.0;
     p->last_launches = 0;
     p->last_kernel_seconds = 0.0;
-    if (time_M < time_m) return 0;
-
-    // kernel choice
     const bool can_tma = tma_supported(p->g);
     int want = p->opt_kernel;
     if (want == 0) want = can_tma ? 2 : 1;
@@ -428,57 +515,99 @@ extern "C" int fdtd_b200_plan_run(fdtd_b200_plan *p, int time_m, int time_M, str
         if (rc) return rc;
     }
     p->kernel_used = want;
-
+    if ((p->link.peer_u[0] || p->link.peer_u[1]) && want != 2) return (int)cudaErrorNotSupported;  // slabs need the streaming kernel
     if (p->ncells_all > 0) {  // m at every source's base corner (m may have been re-uploaded)
         int rc = launch_gather_mbase(p->d_m, p->d_base_idx, p->d_mbase, p->n_mbase, p->stream);
         if (rc) return rc;
         p->last_launches++;
     }
+    return 0;
+}
 
+// The time loop over one or several slabs driven by this process.  Step order is slab-major inside a
+// time step, so slabs that share a device (and stream) serialise and slabs on different devices overlap.
+static int run_many(fdtd_b200_plan **ps, int n, int time_m, int time_M, struct profiler *timers)
+{
+    if (timers) timers->section0 = timers->section1 = 0.0;
+    if (time_M < time_m) return 0;
+    for (int i = 0; i < n; ++i) {
+        int rc = plan_prepare(ps[i]);
+        if (rc) return rc;
+    }
     const int first_timed = time_m + FDTD_WARMUP_STEPS;  // openacc.cpp:90-92,148
     const int ntimed = time_M >= first_timed ? time_M - first_timed + 1 : 0;
-    std::vector<cudaEvent_t> ev;
-    auto stamp = [&]() {
-        cudaEvent_t e = nullptr;
-        cudaEventCreate(&e);
-        cudaEventRecord(e, p->stream);
-        ev.push_back(e);
-        return e;
-    };
-
+    std::vector<RunState> st(n);
     int rc = 0;
-    cudaEvent_t e_begin = nullptr, e_end = nullptr;
-    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> s1_spans;  // Section1 = stand-alone scatter launches only
     for (int time = time_m; time <= time_M && !rc; ++time) {
-        if (time >= first_timed) {
-            if (!e_begin) e_begin = stamp();
-            rc = plan_step(p, time, [&](bool begin) {
-                if (begin) s1_spans.push_back({stamp(), nullptr});
-                else s1_spans.back().second = stamp();
-            });
-        } else {
-            rc = plan_step(p, time, [](bool) {});
+        for (int i = 0; i < n && !rc; ++i) {
+            fdtd_b200_plan *p = ps[i];
+            RunState &r = st[i];
+            if (n > 1) cudaSetDevice(p->dev);
+            if (time >= first_timed) {
+                if (!r.e_begin) r.e_begin = r.stamp(p->stream);
+                rc = plan_step(p, time, time == time_m, [&](bool begin) {
+                    if (begin) r.s1_spans.push_back({r.stamp(p->stream), nullptr});
+                    else r.s1_spans.back().second = r.stamp(p->stream);
+                });
+            } else {
+                rc = plan_step(p, time, time == time_m, [](bool) {});
+            }
         }
     }
-    if (!rc && e_begin) e_end = stamp();
-    cudaError_t es = cudaStreamSynchronize(p->stream);
-    if (!rc && es != cudaSuccess) rc = (int)es;
-    if (!rc && e_begin && e_end) {
-        float ms = 0.f;
-        cudaEventElapsedTime(&ms, e_begin, e_end);
-        double total = ms * 1e-3, s1 = 0.0;
-        for (auto &sp : s1_spans) {
-            if (!sp.second) continue;
-            float m1 = 0.f;
-            cudaEventElapsedTime(&m1, sp.first, sp.second);
-            s1 += m1 * 1e-3;
-        }
-        if (timers) {
-            timers->section0 = total - s1;
-            timers->section1 = s1;
-        }
-        p->last_kernel_seconds = ntimed > 0 ? (total - s1) / ntimed : 0.0;
+    for (int i = 0; i < n; ++i) {
+        if (n > 1) cudaSetDevice(ps[i]->dev);
+        if (!rc && st[i].e_begin) st[i].e_end = st[i].stamp(ps[i]->stream);
     }
-    for (cudaEvent_t e : ev) cudaEventDestroy(e);
+    double worst_total = 0.0, worst_s1 = 0.0;
+    for (int i = 0; i < n; ++i) {
+        fdtd_b200_plan *p = ps[i];
+        RunState &r = st[i];
+        if (n > 1) cudaSetDevice(p->dev);
+        cudaError_t es = cudaStreamSynchronize(p->stream);
+        if (!rc && es != cudaSuccess) rc = (int)es;
+        if (!rc && r.e_begin && r.e_end) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, r.e_begin, r.e_end);
+            double total = ms * 1e-3, s1 = 0.0;
+            for (auto &sp : r.s1_spans) {
+                if (!sp.second) continue;
+                float m1 = 0.f;
+                cudaEventElapsedTime(&m1, sp.first, sp.second);
+                s1 += m1 * 1e-3;
+            }
+            p->last_kernel_seconds = ntimed > 0 ? (total - s1) / ntimed : 0.0;
+            if (total > worst_total) {  // report the slowest slab (device time, max over slabs)
+                worst_total = total;
+                worst_s1 = s1;
+            }
+        }
+        for (cudaEvent_t e : r.ev) cudaEventDestroy(e);
+        if (!rc && (p->link.peer_u[0] || p->link.peer_u[1])) {  // did a neighbour fail to deliver its planes in time?
+            int err = 0;
+            cudaMemcpy(&err, p->link.err, sizeof(int), cudaMemcpyDeviceToHost);
+            if (err) {
+                cudaMemset(p->link.err, 0, sizeof(int));
+                rc = (int)cudaErrorLaunchTimeout;
+            }
+        }
+    }
+    if (!rc && timers) {
+        timers->section0 = worst_total - worst_s1;
+        timers->section1 = worst_s1;
+    }
     return rc;
+}
+
+extern "C" int fdtd_b200_plan_run(fdtd_b200_plan *p, int time_m, int time_M, struct profiler *timers)
+{
+    if (!p) return (int)cudaErrorInvalidValue;
+    return run_many(&p, 1, time_m, time_M, timers);
+}
+
+extern "C" int fdtd_b200_run_slabs(fdtd_b200_plan **plans, int nplans, int time_m, int time_M, struct profiler *timers)
+{
+    if (!plans || nplans < 1) return (int)cudaErrorInvalidValue;
+    for (int i = 0; i < nplans; ++i)
+        if (!plans[i]) return (int)cudaErrorInvalidValue;
+    return run_many(plans, nplans, time_m, time_M, timers);
 }

@@ -23,6 +23,7 @@ struct fdtd_b200_plan {
     fdtd::PlanShape shape{};
     int dev = 0, sm_count = 148;
     cudaStream_t stream = nullptr;
+    bool owns_stream = true;
     fdtd::Grid g{};
     fdtd::Coef k{};
     float *d_u = nullptr, *d_m = nullptr;
@@ -42,6 +43,13 @@ struct fdtd_b200_plan {
     fdtd::TmaConfig cfg{};
     fdtd::TmaPlan tma{};
     int kernel_used = 0;
+
+    // x-slab neighbours: flag words live in the tail of the u allocation (one IPC handle covers both)
+    int *d_flags = nullptr;          // [0] ready-from-lower, [1] ready-from-upper, [2..3] CTA counters, [4] error
+    size_t flags_offset = 0;         // byte offset of d_flags inside the u allocation
+    fdtd::SlabLink link{};           // peers (null = physical boundary)
+    void *ipc_base[2] = {nullptr, nullptr};  // mappings opened with cudaIpcOpenMemHandle
+    int epoch = 0;                   // step sequence number, identical on every slab
 
     // statistics of the last run
     long last_launches = 0;

@@ -81,6 +81,26 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map
         ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
+// Spin (bounded) until *flag >= want; the neighbour stores the flag with release.sys after its
+// boundary planes have landed in this GPU's memory.  On timeout mark *err and carry on.
+__device__ __forceinline__ void wait_flag(const int *flag, int want, int *err)
+{
+    int v, tries = 0;
+    for (;;) {
+        asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if (v >= want) break;
+        __nanosleep(200);
+        if (++tries > 5000000) {  // > 1 s: the neighbour is gone
+            atomicExch(err, 1);
+            break;
+        }
+    }
+    asm volatile("fence.proxy.async;" ::: "memory");  // the ghost planes are read by TMA (async proxy)
+}
+__device__ __forceinline__ void raise_flag(int *flag, int value)
+{
+    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(flag), "r"(value) : "memory");
+}
 __device__ __forceinline__ float4 lds128(const float *p) { return *reinterpret_cast<const float4 *>(p); }
 __device__ __forceinline__ float2 lds64(const float *p) { return *reinterpret_cast<const float2 *>(p); }
 
@@ -155,9 +175,14 @@ __global__ void __launch_bounds__(TileShape<TY, TZ, RY, NS>::NT, MINB)
 
     const Grid &g = a.s.g;
     const int tz = blockIdx.x % a.tiles_z, ty = blockIdx.x / a.tiles_z;
-    const int Xa = g.X0 + blockIdx.y * a.xchunk;
+    // chunk order: the two chunks that hold the slab's boundary planes are dispatched first, so the
+    // neighbours' ghost planes are written (and their flags raised) early in the step
+    const int nch = gridDim.y, by = blockIdx.y;
+    const int chunk = by == 0 ? 0 : (by == 1 ? nch - 1 : by - 1);
+    const int Xa = g.X0 + chunk * a.xchunk;
     const int Xb = min(g.X1, Xa + a.xchunk);
     const int np = Xb - Xa;         // output planes of this CTA (>= 1 by construction)
+    const SlabLink &lk = a.s.link;
     const int Yt = g.Y0 + ty * TY;  // padded origin of the tile
     const int Zt = g.Z0 + tz * TZ;
 
@@ -175,7 +200,14 @@ __global__ void __launch_bounds__(TileShape<TY, TZ, RY, NS>::NT, MINB)
         if (threadIdx.x == T::NC) {
             const int nst = np + 4;
             int slot = 0, use = 0, cslot = 0;
+            bool waited[2] = {!(lk.wait && lk.peer_u[0]), !(lk.wait && lk.peer_u[1])};
             for (int s = 0; s < nst; ++s) {
+                const int Xp = Xa - 2 + s;  // u[t0] plane of this stage: a ghost plane outside [X0, X1)
+                const int side = Xp < g.X0 ? 0 : (Xp >= g.X1 ? 1 : -1);
+                if (side >= 0 && !waited[side]) {
+                    wait_flag(lk.my_flag[side], lk.epoch - 1, lk.err);
+                    waited[side] = true;
+                }
                 if (use > 0) mbar_wait(empty0 + 8 * slot, (use - 1) & 1);
                 const uint32_t bar = full0 + 8 * slot;
                 const bool ctr = s >= 4;
@@ -224,6 +256,11 @@ __global__ void __launch_bounds__(TileShape<TY, TZ, RY, NS>::NT, MINB)
             }
         }
     }
+
+    // boundary planes also go to the neighbours' ghost planes (peer stores over NVLink)
+    const bool cta_lo = lk.peer_u[0] != nullptr && Xa < g.X0 + 2;
+    const bool cta_hi = lk.peer_u[1] != nullptr && Xb > g.X1 - 2;
+    const long long row0 = (long long)Y * g.nzp + Z;
 
     int ms = 0;  // centre-ring slot j % S1
     float *__restrict__ out = a.s.u + (long long)a.s.t2 * g.lvl + ((long long)Xa * g.nyp + Y) * g.nzp + Z;
@@ -302,7 +339,41 @@ __global__ void __launch_bounds__(TileShape<TY, TZ, RY, NS>::NT, MINB)
             for (int r = 0; r < RY; ++r)
                 if (z_ok && Y + r < g.Y1) *reinterpret_cast<float4 *>(out + (long long)r * g.nzp) = o[r];
             out += plane;
+            if (cta_lo || cta_hi) {
+                const int X = Xa + j;
+                if (cta_lo && X < g.X0 + 2) {
+                    float *dst = lk.peer_u[0] + a.s.t2 * lk.peer_lvl[0] + (long long)(lk.peer_plane[0] + X - g.X0) * plane + row0;
+#pragma unroll
+                    for (int r = 0; r < RY; ++r)
+                        if (z_ok && Y + r < g.Y1) *reinterpret_cast<float4 *>(dst + (long long)r * g.nzp) = o[r];
+                }
+                if (cta_hi && X >= g.X1 - 2) {
+                    float *dst = lk.peer_u[1] + a.s.t2 * lk.peer_lvl[1] + (long long)(lk.peer_plane[1] + X - (g.X1 - 2)) * plane + row0;
+#pragma unroll
+                    for (int r = 0; r < RY; ++r)
+                        if (z_ok && Y + r < g.Y1) *reinterpret_cast<float4 *>(dst + (long long)r * g.nzp) = o[r];
+                }
+            }
             if (++ms == S1) ms = 0;
+        }
+    }
+
+    if (cta_lo || cta_hi) {
+        // every consumer thread of this CTA has issued its peer stores: count the CTA, and let the last
+        // CTA of a boundary publish the step's epoch in the neighbour's flag
+        asm volatile("bar.sync 1, %0;" ::"r"(T::NC) : "memory");
+        if (threadIdx.x == 0) {
+            __threadfence_system();
+#pragma unroll
+            for (int side = 0; side < 2; ++side) {
+                if (!(side == 0 ? cta_lo : cta_hi)) continue;
+                const int done = atomicAdd(lk.counter + side, 1);
+                if (done == lk.expect[side] - 1) {
+                    atomicExch(lk.counter + side, 0);
+                    __threadfence_system();
+                    raise_flag(lk.peer_flag[side], lk.epoch);
+                }
+            }
         }
     }
 }
@@ -429,9 +500,9 @@ int tma_plan_build(TmaPlan &p, float *u, const float *m, const Grid &g, const Tm
             if ((nx + xc - 1) / xc != nch) continue;  // not a distinct chunking
             const double waves = tiles * (double)nch / slots;
             const double full = ceil(waves);
-            double eff = waves / full;                       // last-wave quantisation
-            eff *= full / (full + 0.35);                     // ramp-up/drain of the launch amortised over the waves
-            eff /= 1.0 + 0.25 * 4.0 / xc + 1.5 / (xc + 4.0); // prologue re-reads + pipeline fill latency
+            double eff = waves / full;          // last-wave quantisation
+            eff *= full / (full + 0.25);        // ramp-up / drain of the launch, amortised over the waves
+            eff *= xc / (xc + 3.0);             // pipeline prologue of every chunk (4 extra u[t0] planes + fill latency)
             if (eff > best) {
                 best = eff;
                 xchunk = xc;
@@ -466,6 +537,11 @@ int launch_stencil_tma(const TmaPlan &p, const StepArgs &a, bool exact, cudaStre
     args.xchunk = p.xchunk;
     dim3 grid(args.tiles_z * args.tiles_y, (nx + p.xchunk - 1) / p.xchunk, 1);
     if (grid.y > 65535) return (int)cudaErrorInvalidValue;
+    // CTAs whose chunk holds one of the two lowest / two highest planes of the slab
+    const int nchunks = (int)grid.y, last_len = nx - (nchunks - 1) * p.xchunk;
+    const int tiles = (int)grid.x;
+    args.s.link.expect[0] = tiles * ((p.xchunk >= 2 || nchunks == 1) ? 1 : 2);
+    args.s.link.expect[1] = tiles * ((last_len >= 2 || nchunks == 1) ? 1 : 2);
     v.fn<<<grid, v.nt, v.smem, stream>>>(args);
     return (int)cudaGetLastError();
 }

@@ -109,9 +109,13 @@ def lib():
     L.fdtd_b200_plan_ipc_export.restype, L.fdtd_b200_plan_ipc_export.argtypes = i, [vp, vp]
     L.fdtd_b200_plan_ipc_attach.restype, L.fdtd_b200_plan_ipc_attach.argtypes = i, [vp, i, vp]
     L.fdtd_b200_plan_attach_local.restype, L.fdtd_b200_plan_attach_local.argtypes = i, [vp, i, vp]
+    L.fdtd_b200_run_slabs.restype, L.fdtd_b200_run_slabs.argtypes = i, [C.POINTER(vp), i, i, i, C.POINTER(Profiler)]
     L.fdtd_b200_source_table.restype = i
     L.fdtd_b200_source_table.argtypes = [C.POINTER(f)] * 3 + [C.POINTER(i)] * 2 + [C.POINTER(i), C.POINTER(f),
                                                                                     C.POINTER(f), C.POINTER(i)]
+    L.fdtd_b200_slab_source_cells.restype = i
+    L.fdtd_b200_slab_source_cells.argtypes = [C.POINTER(Geometry), vp, i, i, i, i, i, vp, C.POINTER(i), C.POINTER(i), i, vp, vp,
+                                              C.POINTER(i), vp]
     L.fdtd_b200_fill_ricker.restype, L.fdtd_b200_fill_ricker.argtypes = None, [vp, i, i, f]
     L.fdtd_b200_fill_source_coords.restype, L.fdtd_b200_fill_source_coords.argtypes = None, [vp, i, i, i, i, f, f, f]
     L.fdtd_b200_write_benchmark_csv.restype = i
@@ -130,7 +134,7 @@ def exported_symbols():
         "fdtd_b200_plan_fill_dense", "fdtd_b200_plan_set_sources", "fdtd_b200_plan_run",
         "fdtd_b200_plan_last_launches", "fdtd_b200_plan_last_kernel_seconds", "fdtd_b200_plan_set_option",
         "fdtd_b200_plan_get_option", "fdtd_b200_plan_ipc_export", "fdtd_b200_plan_ipc_attach",
-        "fdtd_b200_plan_attach_local", "fdtd_b200_source_table", "fdtd_b200_fill_ricker",
+        "fdtd_b200_plan_attach_local", "fdtd_b200_run_slabs", "fdtd_b200_source_table", "fdtd_b200_slab_source_cells", "fdtd_b200_fill_ricker",
         "fdtd_b200_fill_source_coords", "fdtd_b200_write_benchmark_csv", "fdtd_b200_version",
     ]
 
@@ -211,6 +215,23 @@ def source_table(coord, o, h, lo, hi):
            "fdtd_b200_source_table")
     return (np.array(pos[:], np.int32), np.array(frac[:], np.float32), np.array(w[:], np.float32),
             np.array(inr[:], np.int32))
+
+
+def slab_source_cells(geom: Geometry, coords, p_src_m=0, p_src_M=None):
+    """Host-only scatter table of one slab -> (cells[n,5], ncells_int, contrib_p, contrib_w, base_idx)."""
+    coords = np.ascontiguousarray(coords, np.float32)
+    p_src_M = coords.shape[0] - 1 if p_src_M is None else p_src_M
+    nsrc = max(0, p_src_M - p_src_m + 1)
+    cells = np.zeros((8 * nsrc + 1, 5), np.int32)
+    cp = np.zeros(8 * nsrc + 1, np.int32)
+    cw = np.zeros(8 * nsrc + 1, np.float32)
+    base = np.full(p_src_M + 2, -1, np.int64)
+    n_int, n_all, n_c = C.c_int(), C.c_int(), C.c_int()
+    _check(lib().fdtd_b200_slab_source_cells(C.byref(geom), coords.ctypes.data, coords.shape[0], coords.shape[1], p_src_m,
+                                             p_src_M, cells.shape[0], cells.ctypes.data, C.byref(n_int), C.byref(n_all),
+                                             cp.shape[0], cp.ctypes.data, cw.ctypes.data, C.byref(n_c), base.ctypes.data),
+           "fdtd_b200_slab_source_cells")
+    return cells[:n_all.value], n_int.value, cp[:n_c.value], cw[:n_c.value], base[:p_src_M + 1]
 
 
 def write_benchmark_csv(filename, method, total, s0, s1, device, overhead, gflops, gbps, peak_fp32_gf, peak_bw_gbs,
@@ -324,3 +345,11 @@ class Plan:
 
     def attach_local(self, side: int, other: "Plan"):
         _check(lib().fdtd_b200_plan_attach_local(self._h, side, other._h), "fdtd_b200_plan_attach_local")
+
+
+def run_slabs(plans, time_m: int, time_M: int) -> Profiler:
+    """Advance several slabs driven by this process in lock step (fdtd_b200_run_slabs)."""
+    arr = (C.c_void_p * len(plans))(*[p.handle for p in plans])
+    t = Profiler(0.0, 0.0)
+    _check(lib().fdtd_b200_run_slabs(arr, len(plans), time_m, time_M, C.byref(t)), "fdtd_b200_run_slabs")
+    return t

@@ -148,9 +148,8 @@ def run_b200_arm(a):
         from_slab = None
         plan = pkg.Plan(n, n, n, deviceid=local)
     else:
-        from slab import SlabRun  # x-slab decomposition over torch.distributed (one process per GPU)
-
-        from_slab = SlabRun(pkg, dist, nx_global=n * world, ny=n, nz=n, device=local)
+        # x-slab decomposition, one process per GPU; torch.distributed only carries the rendezvous
+        from_slab = pkg.SlabRun(dist, n * world, n, n, local)
         plan = from_slab.plan
     nxg = n * world
     for k, v in (("exact", a.exact), ("kernel", a.kernel)):
@@ -168,6 +167,7 @@ def run_b200_arm(a):
     def one_step():
         plan.fill(0.0, 1.5)
         if from_slab is not None:
+            dist.barrier()  # a neighbour's first step already writes ghost planes into this slab
             return from_slab.run(0, T - 1)
         return plan.run(0, T - 1)
 

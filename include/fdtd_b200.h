@@ -148,12 +148,26 @@ int fdtd_b200_plan_ipc_attach(fdtd_b200_plan *plan, int side, const void *blob);
 /* Same-process attachment (several slabs driven by one process, peer access enabled). */
 int fdtd_b200_plan_attach_local(fdtd_b200_plan *plan, int side, fdtd_b200_plan *neighbour);
 
+/*
+ * Run the same time steps on several slabs driven by ONE process (one plan per device, or several
+ * plans on one device for tests), neighbours attached with fdtd_b200_plan_attach_local.  timers
+ * receive the slowest slab's device seconds.
+ */
+int fdtd_b200_run_slabs(fdtd_b200_plan **plans, int nplans, int time_m, int time_M, struct profiler *timers);
+
 /* ---- host-only helpers (no GPU needed) */
 
 /* Source table of openacc.cpp:125-134 for one source: pos[3], frac[3], 8 corner weights
  * w[rx*4+ry*2+rz] = 1e-2f*wx*wy*wz, in_range[8] per openacc.cpp:132. */
 int fdtd_b200_source_table(const float coord[3], const float o[3], const float h[3], const int lo[3],
                            const int hi[3], int pos[3], float frac[3], float w[8], int in_range[8]);
+/* The scatter table a slab would build from these sources (host only): cells[i] = {X, Y, Z, first, count}
+ * in padded local coordinates, the first *ncells_int cells lie inside the Section0 write range; every
+ * cell sums contrib_w[first..first+count) * src[t][contrib_p[..]] / m[base_idx[p]] in that order. */
+int fdtd_b200_slab_source_cells(const fdtd_b200_geometry *geom, const float *coords, int ncoords, int cstride,
+                                int p_src_m, int p_src_M, int max_cells, int *cells, int *ncells_int,
+                                int *ncells_all, int max_contribs, int *contrib_p, float *contrib_w,
+                                int *ncontribs, long long *base_idx);
 /* The driver's input generators (main.cpp:290-298 and 301-325), fp32. */
 void fdtd_b200_fill_ricker(float *src, int T, int S, float dt);
 void fdtd_b200_fill_source_coords(float *coords, int S, int nx, int ny, int nz, float h_x, float h_y,

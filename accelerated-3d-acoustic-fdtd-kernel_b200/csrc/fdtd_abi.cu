@@ -3,8 +3,11 @@
 #include "fdtd_plan.h"
 
 #include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
+#include <chrono>
 #include <fstream>
 
 using namespace fdtd;
@@ -37,10 +40,20 @@ static int kernel_entry(struct dataobj *m_vec, struct dataobj *src_vec, struct d
     s.gx_M = x_M;
     s.deviceid = deviceid;
 
+    // FDTD_B200_TRACE=1 prints the host-side phases of the call (staging dominates at large grids)
+    const char *tr = getenv("FDTD_B200_TRACE");
+    const bool trace = tr && *tr == '1';
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+        return std::chrono::duration<double, std::milli>(b - a).count();
+    };
+    const auto t_a = now();
     fdtd_b200_plan *p = nullptr;
-    int rc = plan_create_internal(s, &p);
+    int rc = plan_create_internal(s, &p, /*cache_buffers=*/true);
     if (rc) return rc;
+    const auto t_b = now();
     rc = fdtd_b200_plan_upload(p, (const float *)u_vec->data, (const float *)m_vec->data);
+    const auto t_c = now();
     // "no sources" is p_src_M < p_src_m, an empty src array, or null data (main.cpp:537-545,556)
     const bool has_src = src_vec && src_coords_vec && src_vec->size && src_coords_vec->size && src_vec->data &&
                          src_coords_vec->data && src_vec->size[0] * src_vec->size[1] > 0 && p_src_M - p_src_m + 1 > 0;
@@ -48,9 +61,15 @@ static int kernel_entry(struct dataobj *m_vec, struct dataobj *src_vec, struct d
         rc = fdtd_b200_plan_set_sources(p, (const float *)src_vec->data, src_vec->size[0], src_vec->size[1],
                                         (const float *)src_coords_vec->data, src_coords_vec->size[0],
                                         src_coords_vec->size[1], p_src_m, p_src_M);
+    const auto t_d = now();
     if (!rc) rc = fdtd_b200_plan_run(p, time_m, time_M, timers);
+    const auto t_e = now();
     if (!rc) rc = fdtd_b200_plan_download(p, (float *)u_vec->data);
+    const auto t_f = now();
     fdtd_b200_plan_destroy(p);
+    if (trace)
+        fprintf(stderr, "[fdtd_b200] create %.2f ms | H2D %.2f | sources %.2f | run %.2f | D2H %.2f | destroy %.2f (rc=%d)\n",
+                ms(t_a, t_b), ms(t_b, t_c), ms(t_c, t_d), ms(t_d, t_e), ms(t_e, t_f), ms(t_f, now()), rc);
     return rc;
 }
 

@@ -16,6 +16,7 @@
 #include <algorithm>
 #include <fstream>
 #include <map>
+#include <mutex>
 #include <tuple>
 #include <vector>
 
@@ -87,7 +88,44 @@ static void plan_free_sources(fdtd_b200_plan *p)
     p->src_size0 = 0;
 }
 
-int fdtd::plan_create_internal(const PlanShape &s, fdtd_b200_plan **out)
+// ---------------------------------------------------------------------------- device-buffer cache
+// One entry per process: the (u, m) buffers of the last Kernel_* call, reused when the next call has the
+// same device and sizes (main.cpp runs 5 repetitions per grid).  Invisible to the caller: contents are
+// always overwritten by the upload, the flag words are re-zeroed.  FDTD_B200_NO_CACHE=1 disables it.
+namespace {
+struct BufferCache {
+    std::mutex mu;
+    int dev = -1;
+    size_t u_bytes = 0, m_bytes = 0;
+    float *d_u = nullptr, *d_m = nullptr;
+} g_cache;
+
+bool cache_take(int dev, size_t u_bytes, size_t m_bytes, float **d_u, float **d_m)
+{
+    std::lock_guard<std::mutex> lk(g_cache.mu);
+    if (!g_cache.d_u || g_cache.dev != dev || g_cache.u_bytes != u_bytes || g_cache.m_bytes != m_bytes) return false;
+    *d_u = g_cache.d_u;
+    *d_m = g_cache.d_m;
+    g_cache.d_u = g_cache.d_m = nullptr;
+    return true;
+}
+
+void cache_give(int dev, size_t u_bytes, size_t m_bytes, float *d_u, float *d_m)
+{
+    std::lock_guard<std::mutex> lk(g_cache.mu);
+    if (g_cache.d_u) {  // a different size is parked: drop it
+        cudaFree(g_cache.d_u);
+        cudaFree(g_cache.d_m);
+    }
+    g_cache.dev = dev;
+    g_cache.u_bytes = u_bytes;
+    g_cache.m_bytes = m_bytes;
+    g_cache.d_u = d_u;
+    g_cache.d_m = d_m;
+}
+}  // namespace
+
+int fdtd::plan_create_internal(const PlanShape &s, fdtd_b200_plan **out, bool cache_buffers)
 {
     if (!out) return (int)cudaErrorInvalidValue;
     *out = nullptr;
@@ -131,7 +169,12 @@ int fdtd::plan_create_internal(const PlanShape &s, fdtd_b200_plan **out)
 
     cudaError_t e = cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking);
     p->flags_offset = (3 * (size_t)p->g.lvl * sizeof(float) + 255) / 256 * 256;
-    if (e == cudaSuccess) e = cudaMalloc(&p->d_u, p->flags_offset + 256);
+    p->u_bytes = p->flags_offset + 256;
+    p->m_bytes = (size_t)p->g.lvl * sizeof(float);
+    const char *nc = getenv("FDTD_B200_NO_CACHE");
+    p->cache_buffers = cache_buffers && !(nc && *nc == '1');
+    const bool reused = p->cache_buffers && cache_take(p->dev, p->u_bytes, p->m_bytes, &p->d_u, &p->d_m);
+    if (e == cudaSuccess && !reused) e = cudaMalloc(&p->d_u, p->u_bytes);
     if (e == cudaSuccess) {
         p->d_flags = reinterpret_cast<int *>(reinterpret_cast<char *>(p->d_u) + p->flags_offset);
         e = cudaMemset(p->d_flags, 0, 256);
@@ -140,7 +183,7 @@ int fdtd::plan_create_internal(const PlanShape &s, fdtd_b200_plan **out)
         p->link.counter = p->d_flags + 2;
         p->link.err = p->d_flags + 4;
     }
-    if (e == cudaSuccess) e = cudaMalloc(&p->d_m, (size_t)p->g.lvl * sizeof(float));
+    if (e == cudaSuccess && !reused) e = cudaMalloc(&p->d_m, p->m_bytes);
     if (e != cudaSuccess) {
         fdtd_b200_plan_destroy(p);
         return (int)e;
@@ -165,8 +208,13 @@ extern "C" int fdtd_b200_plan_destroy(fdtd_b200_plan *p)
     plan_free_sources(p);
     for (int s = 0; s < 2; ++s)
         if (p->ipc_base[s]) cudaIpcCloseMemHandle(p->ipc_base[s]);
-    cudaFree(p->d_u);
-    cudaFree(p->d_m);
+    if (p->cache_buffers && p->d_u && p->d_m) {
+        if (p->stream) cudaStreamSynchronize(p->stream);
+        cache_give(p->dev, p->u_bytes, p->m_bytes, p->d_u, p->d_m);
+    } else {
+        cudaFree(p->d_u);
+        cudaFree(p->d_m);
+    }
     if (p->stream && p->owns_stream) cudaStreamDestroy(p->stream);
     delete p;
     return 0;
@@ -508,7 +556,11 @@ static int plan_prepare(fdtd_b200_plan *p)
     p->last_kernel_seconds = 0.0;
     const bool can_tma = tma_supported(p->g);
     int want = p->opt_kernel;
-    if (want == 0) want = can_tma ? 2 : 1;
+    // auto: the streaming kernel needs enough planes x tiles to hide its per-plane latency chain; below ~110^3
+    // points a step is a few microseconds and the one-point-per-thread kernel wins (profiles/r01_small_grids.txt)
+    const long long npts = (long long)(p->g.X1 - p->g.X0) * (p->g.Y1 - p->g.Y0) * (p->g.Z1 - p->g.Z0);
+    const bool linked = p->link.peer_u[0] || p->link.peer_u[1];
+    if (want == 0) want = (can_tma && (npts >= 1400000 || linked)) ? 2 : 1;
     if (want == 2 && !can_tma) return (int)cudaErrorInvalidValue;
     if (want == 2 && !p->tma.valid) {
         int rc = tma_plan_build(p->tma, p->d_u, p->d_m, p->g, p->cfg, p->opt_exact != 0, p->sm_count);

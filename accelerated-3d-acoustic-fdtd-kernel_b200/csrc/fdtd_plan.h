@@ -15,7 +15,10 @@ struct PlanShape {
     int deviceid;
 };
 
-int plan_create_internal(const PlanShape &s, fdtd_b200_plan **out);
+// cache_buffers: take the field buffers from / return them to the per-process device-buffer cache (used by
+// the Kernel_* entry points, whose callers run the same size repeatedly: cudaMalloc/cudaFree of GBs costs
+// more than the 50 time steps).
+int plan_create_internal(const PlanShape &s, fdtd_b200_plan **out, bool cache_buffers = false);
 
 }  // namespace fdtd
 
@@ -27,6 +30,8 @@ struct fdtd_b200_plan {
     fdtd::Grid g{};
     fdtd::Coef k{};
     float *d_u = nullptr, *d_m = nullptr;
+    bool cache_buffers = false;
+    size_t u_bytes = 0, m_bytes = 0;
 
     // sources: cells [0, ncells_int) are inside the Section0 write range (fusable), the rest are halo cells
     float *d_src = nullptr;

@@ -24,12 +24,11 @@ __global__ void __launch_bounds__(256) stencil_generic_kernel(StepArgs a)
     const float *__restrict__ u1 = a.u + a.t1 * a.g.lvl;
     float *__restrict__ u2 = a.u + a.t2 * a.g.lvl;
 
-    const float uc = __ldg(u0 + c);
-    const float r5 = EXACT ? __fmul_rn(FDTD_C0, uc) : FDTD_C0 * uc;
-    const float dx = axis_term<EXACT>(r5, __ldg(u0 + c - 2 * sx), __ldg(u0 + c - sx), __ldg(u0 + c + sx), __ldg(u0 + c + 2 * sx));
-    const float dy = axis_term<EXACT>(r5, __ldg(u0 + c - 2 * sy), __ldg(u0 + c - sy), __ldg(u0 + c + sy), __ldg(u0 + c + 2 * sy));
-    const float dz = axis_term<EXACT>(r5, __ldg(u0 + c - 2), __ldg(u0 + c - 1), __ldg(u0 + c + 1), __ldg(u0 + c + 2));
-    float v = leapfrog<EXACT>(uc, dx, dy, dz, __ldg(u1 + c), __ldg(a.m + c), a.k);
+    // the same per-point function as the streaming kernel: both kernels agree bit for bit in both modes
+    float v = point<EXACT>(__ldg(u0 + c), __ldg(u0 + c - 2 * sx), __ldg(u0 + c - sx), __ldg(u0 + c + sx), __ldg(u0 + c + 2 * sx),
+                           __ldg(u0 + c - 2 * sy), __ldg(u0 + c - sy), __ldg(u0 + c + sy), __ldg(u0 + c + 2 * sy),
+                           __ldg(u0 + c - 2), __ldg(u0 + c - 1), __ldg(u0 + c + 1), __ldg(u0 + c + 2), __ldg(u1 + c),
+                           __ldg(a.m + c), a.k);
 
     if (a.sv.ncells > 0) {  // fused Section1: the owner of a source cell adds its contributions
         const int c0 = a.sv.plane_off[X], c1 = a.sv.plane_off[X + 1];

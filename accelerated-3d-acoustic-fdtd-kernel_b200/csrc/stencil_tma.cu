@@ -127,33 +127,6 @@ struct TileShape {
     static_assert(CBYTES % 128 == 0, "centre slots must stay 128-byte aligned");
 };
 
-// One output point.  x*/y*/z* are the radius-2 neighbours along each axis.
-template <bool EXACT>
-__device__ __forceinline__ float point(float c, float xm2, float xm1, float xp1, float xp2, float ym2, float ym1,
-                                       float yp1, float yp2, float zm2, float zm1, float zp1, float zp2, float u1,
-                                       float m, const Coef &k)
-{
-    if (EXACT) {
-        const float r5 = __fmul_rn(FDTD_C0, c);
-        const float dx = axis_term<true>(r5, xm2, xm1, xp1, xp2);
-        const float dy = axis_term<true>(r5, ym2, ym1, yp1, yp2);
-        const float dz = axis_term<true>(r5, zm2, zm1, zp1, zp2);
-        return leapfrog<true>(c, dx, dy, dz, u1, m, k);
-    } else {
-        // minimal-operation form: dt^2*lap accumulated with pre-multiplied coefficients, one MUFU.RCP
-        float acc = k.f0 * c;
-        acc = fmaf(k.fx2, xm2 + xp2, acc);
-        acc = fmaf(k.fx1, xm1 + xp1, acc);
-        acc = fmaf(k.fy2, ym2 + yp2, acc);
-        acc = fmaf(k.fy1, ym1 + yp1, acc);
-        acc = fmaf(k.fz2, zm2 + zp2, acc);
-        acc = fmaf(k.fz1, zm1 + zp1, acc);
-        float rm;
-        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rm) : "f"(m));
-        return fmaf(acc, rm, fmaf(2.0f, c, -u1));
-    }
-}
-
 template <int I>
 __device__ __forceinline__ float f4get(const float4 &v)
 {

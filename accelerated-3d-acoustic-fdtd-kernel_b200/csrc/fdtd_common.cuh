@@ -6,6 +6,7 @@
 
 #define FDTD_HALO 4          // reference main.cpp:27-32: HALO == STENCIL_ORDER == 4 cells
 #define FDTD_WARMUP_STEPS 5  // reference openacc.cpp:5
+#define FDTD_LEVELS 4        // device levels of u: the ABI's 3-level ring + 1 work level for two-step passes
 
 #define FDTD_CHECK(expr)                         \
     do {                                         \
@@ -53,7 +54,8 @@ struct SourceView {
 struct SlabLink {
     float *peer_u[2];        // neighbour's u base (peer-mapped); nullptr = physical boundary
     long long peer_lvl[2];   // neighbour's elements per level
-    int peer_plane[2];       // first ghost plane to fill in the neighbour (its X1, resp. its X0-2)
+    int peer_edge[2];        // side 0: the neighbour's X1 (my plane X0+i lands on its ghost plane X1+i);
+                             // side 1: the neighbour's X0 (my plane X1-i lands on its ghost plane X0-i)
     int *peer_flag[2];       // flag in the neighbour's memory that THIS slab raises
     int *my_flag[2];         // flags in this slab's memory raised by the neighbours
     int *counter;            // [2] CTAs of this launch that finished each boundary
@@ -61,6 +63,7 @@ struct SlabLink {
     int expect[2];           // CTAs touching each boundary in this launch
     int epoch;               // sequence number of this step (same on every slab)
     int wait;                // 1: ghost planes of u[t0] were produced by the neighbours' step epoch-1
+    int depth;               // boundary planes pushed per side: 2 (one step per pass), 4 when two-step passes are in use
 };
 
 // Field geometry of one slab as the kernels see it.

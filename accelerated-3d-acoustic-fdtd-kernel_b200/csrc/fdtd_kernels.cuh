@@ -40,6 +40,36 @@ int tma_plan_build(TmaPlan &p, float *u, const float *m, const Grid &g, const Tm
                    int sm_count);
 int launch_stencil_tma(const TmaPlan &p, const StepArgs &a, bool exact, cudaStream_t stream);
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda): fp32, no swizzle, OOB = 0.
+int encode_tensor_map(CUtensorMap *map, const float *base, int rank, const cuuint64_t *dims, const cuuint32_t *box);
+
+// --- two time steps per pass (temporal blocking): u^{n+1} and u^{n+2} from u^{n-1}, u^n and m read once.
+// Levels are indices into the plan's FDTD_LEVELS-deep array.
+struct Tb2Plan {
+    alignas(64) CUtensorMap map_cur;   // u as (z,y,x,level), box (tz+8, ty+8, 1, 1): u^n with the radius-4 halo
+    alignas(64) CUtensorMap map_prev;  // u as (z,y,x,level), box (tz+8, ty+4, 1, 1): u^{n-1} on the extended tile
+    alignas(64) CUtensorMap map_m;     // m as (z,y,x), box (tz+8, ty+4, 1)
+    int ty, tz, xchunk, variant;       // output tile, x planes per CTA
+    size_t smem_bytes;
+    bool valid = false;
+};
+struct Tb2Step {
+    float *u;
+    Grid g;
+    Coef k;
+    int l_prev, l_cur, l_n1, l_n2;     // level indices of u^{n-1}, u^n (inputs) and u^{n+1}, u^{n+2} (outputs)
+    SourceView sv;                     // cells incl. the neighbours' two nearest planes; sv.src_row = src row of step n
+    const float *src_row2;             // src row of step n+1
+    SlabLink link;                     // x-slab neighbours (all null for a single slab)
+};
+constexpr int kSlabEdgePlanes = 8;     // length of the boundary chunks of a slab with neighbours
+int tb2_plan_build(Tb2Plan &p, float *u, const float *m, const Grid &g, const TmaConfig &cfg, bool exact, int sm_count);
+int launch_stencil_tb2(const Tb2Plan &p, const Tb2Step &a, bool exact, cudaStream_t stream);
+// 1 in *flag (device) unless the shells (every padded cell outside g's box) of levels 0..2 are bit-identical
+int launch_shell_check(float *u, const Grid &g, int *flag, cudaStream_t stream);
+// shell of level `from` -> level `to`
+int launch_shell_copy(float *u, const Grid &g, int from, int to, cudaStream_t stream);
+
 // --- Section1 stand-alone scatter: one thread per cell, contributions added in p_src order.
 int launch_scatter(float *u_level, const Grid &g, const SourceCell *cells, int ncells,
                    const SourceContrib *contribs, const float *src_row, const float *mbase,

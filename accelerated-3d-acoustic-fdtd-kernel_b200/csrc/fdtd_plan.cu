@@ -40,6 +40,7 @@ static int env_int(const char *key, int fallback)
     const char *v = getenv(key);
     return (v && *v) ? atoi(v) : fallback;
 }
+static const int g_debug_sync = env_int("FDTD_B200_SYNC", 0);
 
 // ---------------------------------------------------------------------------- source table (host, IEEE fp32)
 // One axis of openacc.cpp:125-131: g = (-o + c)/h ; pos = (int)floor(g) ; frac = -floor(g) + g.
@@ -77,6 +78,12 @@ static void plan_free_sources(fdtd_b200_plan *p)
     cudaFree(p->d_plane_off);
     cudaFree(p->d_mbase);
     cudaFree(p->d_base_idx);
+    cudaFree(p->d_cells2);
+    cudaFree(p->d_plane_off2);
+    p->d_cells2 = nullptr;
+    p->d_plane_off2 = nullptr;
+    p->ncells2 = 0;
+    p->src_halo_global = false;
     p->d_src = nullptr;
     p->d_cells = nullptr;
     p->d_contribs = nullptr;
@@ -165,10 +172,10 @@ int fdtd::plan_create_internal(const PlanShape &s, fdtd_b200_plan **out, bool ca
     p->cfg.rows = env_int("FDTD_B200_ROWS", 0);
     p->cfg.stages = env_int("FDTD_B200_STAGES", 0);
     p->cfg.xchunk = env_int("FDTD_B200_XCHUNK", 0);
-    p->opt_t_fuse = g_t_fuse;
+    p->opt_t_fuse = env_int("FDTD_B200_T_FUSE", g_t_fuse);
 
     cudaError_t e = cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking);
-    p->flags_offset = (3 * (size_t)p->g.lvl * sizeof(float) + 255) / 256 * 256;
+    p->flags_offset = (FDTD_LEVELS * (size_t)p->g.lvl * sizeof(float) + 255) / 256 * 256;
     p->u_bytes = p->flags_offset + 256;
     p->m_bytes = (size_t)p->g.lvl * sizeof(float);
     const char *nc = getenv("FDTD_B200_NO_CACHE");
@@ -222,6 +229,20 @@ extern "C" int fdtd_b200_plan_destroy(fdtd_b200_plan *p)
 
 extern "C" float *fdtd_b200_plan_u(fdtd_b200_plan *p) { return p ? p->d_u : nullptr; }
 extern "C" float *fdtd_b200_plan_m(fdtd_b200_plan *p) { return p ? p->d_m : nullptr; }
+extern "C" float *fdtd_b200_plan_level(fdtd_b200_plan *p, int ring_level)
+{
+    if (!p || ring_level < 0 || ring_level > 2) return nullptr;
+    return p->d_u + (size_t)p->phys[ring_level] * p->g.lvl;
+}
+
+static void reset_placement(fdtd_b200_plan *p, int shell_state)
+{
+    p->phys[0] = 0;
+    p->phys[1] = 1;
+    p->phys[2] = 2;
+    p->work = 3;
+    p->shell_state = shell_state;
+}
 extern "C" size_t fdtd_b200_plan_level_elems(fdtd_b200_plan *p) { return p ? (size_t)p->g.lvl : 0; }
 extern "C" long fdtd_b200_plan_last_launches(fdtd_b200_plan *p) { return p ? p->last_launches : 0; }
 extern "C" double fdtd_b200_plan_last_kernel_seconds(fdtd_b200_plan *p) { return p ? p->last_kernel_seconds : 0.0; }
@@ -230,7 +251,10 @@ extern "C" int fdtd_b200_plan_upload(fdtd_b200_plan *p, const float *h_u, const 
 {
     if (!p) return (int)cudaErrorInvalidValue;
     FDTD_CHECK(cudaSetDevice(p->dev));
-    if (h_u) FDTD_CHECK(cudaMemcpyAsync(p->d_u, h_u, 3 * (size_t)p->g.lvl * sizeof(float), cudaMemcpyHostToDevice, p->stream));
+    if (h_u) {
+        reset_placement(p, 0);
+        FDTD_CHECK(cudaMemcpyAsync(p->d_u, h_u, 3 * (size_t)p->g.lvl * sizeof(float), cudaMemcpyHostToDevice, p->stream));
+    }
     if (h_m) FDTD_CHECK(cudaMemcpyAsync(p->d_m, h_m, (size_t)p->g.lvl * sizeof(float), cudaMemcpyHostToDevice, p->stream));
     FDTD_CHECK(cudaStreamSynchronize(p->stream));
     return 0;
@@ -240,7 +264,13 @@ extern "C" int fdtd_b200_plan_download(fdtd_b200_plan *p, float *h_u)
 {
     if (!p || !h_u) return (int)cudaErrorInvalidValue;
     FDTD_CHECK(cudaSetDevice(p->dev));
-    FDTD_CHECK(cudaMemcpyAsync(h_u, p->d_u, 3 * (size_t)p->g.lvl * sizeof(float), cudaMemcpyDeviceToHost, p->stream));
+    const size_t lvl = (size_t)p->g.lvl;
+    if (p->phys[0] == 0 && p->phys[1] == 1 && p->phys[2] == 2) {
+        FDTD_CHECK(cudaMemcpyAsync(h_u, p->d_u, 3 * lvl * sizeof(float), cudaMemcpyDeviceToHost, p->stream));
+    } else {
+        for (int r = 0; r < 3; ++r)
+            FDTD_CHECK(cudaMemcpyAsync(h_u + r * lvl, p->d_u + p->phys[r] * lvl, lvl * sizeof(float), cudaMemcpyDeviceToHost, p->stream));
+    }
     FDTD_CHECK(cudaStreamSynchronize(p->stream));
     return 0;
 }
@@ -249,7 +279,8 @@ extern "C" int fdtd_b200_plan_fill(fdtd_b200_plan *p, float u_value, float m_val
 {
     if (!p) return (int)cudaErrorInvalidValue;
     FDTD_CHECK(cudaSetDevice(p->dev));
-    int rc = launch_fill(p->d_u, 3 * (size_t)p->g.lvl, u_value, p->stream);
+    reset_placement(p, 1);  // a constant field: every device level (the spare one too) has the same shell
+    int rc = launch_fill(p->d_u, FDTD_LEVELS * (size_t)p->g.lvl, u_value, p->stream);
     if (!rc) rc = launch_fill(p->d_m, (size_t)p->g.lvl, m_value, p->stream);
     if (rc) return rc;
     FDTD_CHECK(cudaStreamSynchronize(p->stream));
@@ -260,6 +291,7 @@ extern "C" int fdtd_b200_plan_fill_dense(fdtd_b200_plan *p)
 {
     if (!p) return (int)cudaErrorInvalidValue;
     FDTD_CHECK(cudaSetDevice(p->dev));
+    reset_placement(p, 0);
     int rc = launch_fill_dense(p->d_u, p->d_m, p->g.nxp, p->g.nyp, p->g.nzp, p->shape.x_offset, p->stream);
     if (rc) return rc;
     FDTD_CHECK(cudaStreamSynchronize(p->stream));
@@ -276,6 +308,10 @@ struct SourceTable {
     std::vector<int> plane_off;        // [nxp+1], interior cells only
     std::vector<long long> base_idx;   // [p_src_M+1] linear index of each source's base corner, -1 = unused
     int ncells_int = 0;
+    // two-step passes: interior cells + cells on the neighbour slabs' two nearest planes, sorted by (X,Y,Z)
+    std::vector<SourceCell> cells2;
+    std::vector<int> plane_off2;       // [nxp+1]
+    bool halo_global = false;          // some in-range corner of some source is a halo cell of the GLOBAL grid
 };
 
 static void build_source_table(const PlanShape &s, const Grid &g, const float *coords, int cstride, int p_src_m,
@@ -286,6 +322,7 @@ static void build_source_table(const PlanShape &s, const Grid &g, const float *c
     const float o[3] = {s.o_x, s.o_y, s.o_z}, h[3] = {s.h_x, s.h_y, s.h_z};
 
     std::map<std::tuple<int, int, int>, std::vector<SourceContrib>> cells;  // ordered by (X,Y,Z); p ascending inside
+    std::map<std::tuple<int, int, int>, std::vector<SourceContrib>> ghosts;  // cells on the neighbours' nearest planes
     t.base_idx.assign((size_t)p_src_M + 1, -1);
     for (int ps = p_src_m; ps <= p_src_M; ++ps) {
         int pos[3], in_range[8];
@@ -299,8 +336,16 @@ static void build_source_table(const PlanShape &s, const Grid &g, const float *c
                     if (!in_range[i]) continue;
                     const int X = rx + pos[0] - s.x_offset + FDTD_HALO;  // local padded plane
                     const int Y = ry + pos[1] + FDTD_HALO, Z = rz + pos[2] + FDTD_HALO;
+                    const int gx = rx + pos[0];  // global unpadded x of this corner
+                    if (gx < s.gx_m || gx > s.gx_M || Y < g.Y0 || Y >= g.Y1 || Z < g.Z0 || Z >= g.Z1) t.halo_global = true;
                     // ownership along the slab axis: interior planes, plus the physical halo plane at a global end
                     const bool owned = (X >= g.X0 && X < g.X1) || (first_slab && X == g.X0 - 1) || (last_slab && X == g.X1);
+                    const bool ghost = !owned && ((!first_slab && X >= g.X0 - 2 && X < g.X0) || (!last_slab && X >= g.X1 && X < g.X1 + 2)) &&
+                                       Y >= g.Y0 && Y < g.Y1 && Z >= g.Z0 && Z < g.Z1;
+                    if (ghost) {
+                        ghosts[std::make_tuple(X, Y, Z)].push_back(SourceContrib{ps, w[i]});
+                        any = true;
+                    }
                     if (!owned) continue;
                     cells[std::make_tuple(X, Y, Z)].push_back(SourceContrib{ps, w[i]});
                     any = true;
@@ -325,6 +370,23 @@ static void build_source_table(const PlanShape &s, const Grid &g, const float *c
     t.ncells_int = (int)cint.size();
     t.cells = cint;
     t.cells.insert(t.cells.end(), chalo.begin(), chalo.end());
+    // interior + ghost cells in (X,Y,Z) order: ghost planes lie below X0 / above X1, so the order is lower ghosts,
+    // interior, upper ghosts
+    std::vector<SourceCell> glo, ghi;
+    for (auto &kv : ghosts) {
+        SourceCell c;
+        std::tie(c.X, c.Y, c.Z) = kv.first;
+        c.first = (int)t.contribs.size();
+        c.count = (int)kv.second.size();
+        t.contribs.insert(t.contribs.end(), kv.second.begin(), kv.second.end());
+        (c.X < g.X0 ? glo : ghi).push_back(c);
+    }
+    t.cells2 = glo;
+    t.cells2.insert(t.cells2.end(), cint.begin(), cint.end());
+    t.cells2.insert(t.cells2.end(), ghi.begin(), ghi.end());
+    t.plane_off2.assign((size_t)g.nxp + 1, 0);
+    for (const SourceCell &c : t.cells2) t.plane_off2[c.X + 1]++;
+    for (int x = 0; x < g.nxp; ++x) t.plane_off2[x + 1] += t.plane_off2[x];
 }
 
 static void shape_from_geometry(const fdtd_b200_geometry *geo, PlanShape &s)
@@ -427,6 +489,18 @@ extern "C" int fdtd_b200_plan_set_sources(fdtd_b200_plan *p, const float *src, i
     FDTD_CHECK(cudaMalloc(&p->d_mbase, (size_t)p->n_mbase * sizeof(float)));
     FDTD_CHECK(cudaMalloc(&p->d_base_idx, (size_t)p->n_mbase * sizeof(long long)));
     FDTD_CHECK(cudaMemcpy(p->d_base_idx, base_idx.data(), (size_t)p->n_mbase * sizeof(long long), cudaMemcpyHostToDevice));
+    p->src_halo_global = tab.halo_global;
+    p->ncells2 = (int)tab.cells2.size();
+    if (!tab.cells2.empty()) {
+        FDTD_CHECK(cudaMalloc(&p->d_cells2, tab.cells2.size() * sizeof(SourceCell)));
+        FDTD_CHECK(cudaMemcpy(p->d_cells2, tab.cells2.data(), tab.cells2.size() * sizeof(SourceCell), cudaMemcpyHostToDevice));
+        FDTD_CHECK(cudaMalloc(&p->d_plane_off2, tab.plane_off2.size() * sizeof(int)));
+        FDTD_CHECK(cudaMemcpy(p->d_plane_off2, tab.plane_off2.data(), tab.plane_off2.size() * sizeof(int), cudaMemcpyHostToDevice));
+    }
+    if (!contribs.empty() && all.empty()) {  // only ghost cells: the contribution list is still needed
+        FDTD_CHECK(cudaMalloc(&p->d_contribs, contribs.size() * sizeof(SourceContrib)));
+        FDTD_CHECK(cudaMemcpy(p->d_contribs, contribs.data(), contribs.size() * sizeof(SourceContrib), cudaMemcpyHostToDevice));
+    }
     if (!all.empty()) {
         FDTD_CHECK(cudaMalloc(&p->d_cells, all.size() * sizeof(SourceCell)));
         FDTD_CHECK(cudaMemcpy(p->d_cells, all.data(), all.size() * sizeof(SourceCell), cudaMemcpyHostToDevice));
@@ -450,6 +524,7 @@ static int *option_slot(fdtd_b200_plan *p, const char *key)
     if (!strcmp(key, "rows")) return &p->cfg.rows;
     if (!strcmp(key, "stages")) return &p->cfg.stages;
     if (!strcmp(key, "xchunk")) return &p->cfg.xchunk;
+    if (!strcmp(key, "t_fuse_agreed")) return &p->t_fuse_agreed;
     return nullptr;
 }
 
@@ -459,6 +534,7 @@ extern "C" int fdtd_b200_plan_set_option(fdtd_b200_plan *p, const char *key, int
     if (!slot) return (int)cudaErrorInvalidValue;
     *slot = value;
     p->tma.valid = false;  // rebuilt lazily by the next run
+    p->tb2.valid = false;
     return 0;
 }
 
@@ -466,11 +542,13 @@ extern "C" int fdtd_b200_plan_get_option(fdtd_b200_plan *p, const char *key, int
 {
     if (!p || !key || !value) return (int)cudaErrorInvalidValue;
     if (!strcmp(key, "kernel_used")) { *value = p->kernel_used; return 0; }
-    if (!strcmp(key, "tile_y_used")) { *value = p->tma.valid ? p->tma.ty : 0; return 0; }
-    if (!strcmp(key, "tile_z_used")) { *value = p->tma.valid ? p->tma.tz : 0; return 0; }
-    if (!strcmp(key, "rows_used")) { *value = p->tma.valid ? p->tma.rows : 0; return 0; }
+    const bool two = p->t_fuse_used == 2 && p->tb2.valid;  // report the two-step kernel's shape when it is the one in use
+    if (!strcmp(key, "t_fuse_used")) { *value = p->t_fuse_used; return 0; }
+    if (!strcmp(key, "tile_y_used")) { *value = two ? p->tb2.ty : (p->tma.valid ? p->tma.ty : 0); return 0; }
+    if (!strcmp(key, "tile_z_used")) { *value = two ? p->tb2.tz : (p->tma.valid ? p->tma.tz : 0); return 0; }
+    if (!strcmp(key, "rows_used")) { *value = two ? 1 : (p->tma.valid ? p->tma.rows : 0); return 0; }
     if (!strcmp(key, "stages_used")) { *value = p->tma.valid ? p->tma.stages : 0; return 0; }
-    if (!strcmp(key, "xchunk_used")) { *value = p->tma.valid ? p->tma.xchunk : 0; return 0; }
+    if (!strcmp(key, "xchunk_used")) { *value = two ? p->tb2.xchunk : (p->tma.valid ? p->tma.xchunk : 0); return 0; }
     if (!strcmp(key, "ncells_fused")) { *value = p->ncells_int; return 0; }
     if (!strcmp(key, "ncells_halo")) { *value = p->ncells_halo; return 0; }
     int *slot = option_slot(p, key);
@@ -495,9 +573,9 @@ static int plan_step(fdtd_b200_plan *p, int time, bool first_of_run, Mark &&mark
     a.m = p->d_m;
     a.g = p->g;
     a.k = p->k;
-    a.t0 = t0;
-    a.t1 = t1;
-    a.t2 = t2;
+    a.t0 = p->phys[t0];  // device levels that hold the ring levels
+    a.t1 = p->phys[t1];
+    a.t2 = p->phys[t2];
     const bool fuse = has_src && p->opt_fuse && p->ncells_int > 0;
     if (fuse) {
         a.sv.plane_off = p->d_plane_off;
@@ -510,6 +588,7 @@ static int plan_step(fdtd_b200_plan *p, int time, bool first_of_run, Mark &&mark
     a.link = p->link;
     a.link.epoch = ++p->epoch;
     a.link.wait = first_of_run ? 0 : 1;  // the first step's ghost planes come from the caller's initial state
+    a.link.depth = p->t_fuse_used == 2 ? 4 : 2;  // a two-step pass may follow: it reads 4 ghost planes of u[t2]
     int rc;
     if (p->kernel_used == 2)
         rc = launch_stencil_tma(p->tma, a, p->opt_exact != 0, p->stream);
@@ -524,7 +603,7 @@ static int plan_step(fdtd_b200_plan *p, int time, bool first_of_run, Mark &&mark
         const int count = p->ncells_all - first;
         if (count > 0) {
             mark(true);
-            rc = launch_scatter(p->d_u + (size_t)t2 * p->g.lvl, p->g, p->d_cells + first, count, p->d_contribs, src_row,
+            rc = launch_scatter(p->d_u + (size_t)p->phys[t2] * p->g.lvl, p->g, p->d_cells + first, count, p->d_contribs, src_row,
                                 p->d_mbase, p->stream);
             if (rc) return rc;
             p->last_launches++;
@@ -532,6 +611,91 @@ static int plan_step(fdtd_b200_plan *p, int time, bool first_of_run, Mark &&mark
         }
     }
     return 0;
+}
+
+// One two-step pass: u^{time+1} and u^{time+2} from u^{time-1}, u^{time} and m read once (stencil_tb2.cu), both
+// steps' source cells fused.  u^{time+2} belongs in ring level t1 (it replaces u^{time-1}) but is written to the
+// spare device level, which then becomes ring level t1.
+static int plan_pass2(fdtd_b200_plan *p, int time, bool first_of_run)
+{
+    const int t0 = ((time % 3) + 3) % 3, t1 = (((time + 2) % 3) + 3) % 3, t2 = (((time + 1) % 3) + 3) % 3;
+    const bool has_src = p->ncells2 > 0 && time >= 0 && time + 1 < p->src_size0;
+    Tb2Step a{};
+    a.u = p->d_u;
+    a.g = p->g;
+    a.k = p->k;
+    a.l_prev = p->phys[t1];
+    a.l_cur = p->phys[t0];
+    a.l_n1 = p->phys[t2];
+    a.l_n2 = p->work;
+    if (has_src) {
+        a.sv.plane_off = p->d_plane_off2;
+        a.sv.cells = p->d_cells2;
+        a.sv.contribs = p->d_contribs;
+        a.sv.src_row = p->d_src + (size_t)time * p->pstride;
+        a.sv.mbase = p->d_mbase;
+        a.sv.ncells = p->ncells2;
+        a.src_row2 = p->d_src + (size_t)(time + 1) * p->pstride;
+    }
+    a.link = p->link;
+    a.link.epoch = ++p->epoch;
+    a.link.wait = first_of_run ? 0 : 1;
+    a.link.depth = 4;
+    int rc = launch_stencil_tb2(p->tb2, a, p->opt_exact != 0, p->stream);
+    if (rc) return rc;
+    p->last_launches++;
+    std::swap(p->phys[t1], p->work);
+    return 0;
+}
+
+// Would steps `time` and `time+1` see the same kind of source row (both injected, or both not)?
+static bool same_source_regime(const fdtd_b200_plan *p, int time)
+{
+    if (p->ncells_all == 0 && p->ncells2 == 0) return true;
+    const bool a = time >= 0 && time < p->src_size0, b = time + 1 >= 0 && time + 1 < p->src_size0;
+    return a == b;
+}
+
+// Depth (1 or 2 time steps per pass) this slab could run with its current options, sources and field -- the
+// local view; linked slabs must agree (fdtd_b200_plan_probe_fuse + the driver's reduction, or run_slabs).
+static int plan_fuse_feasible(fdtd_b200_plan *p, int *out)
+{
+    *out = 1;
+    if (p->opt_t_fuse < 2 || p->opt_kernel == 1 || !tma_supported(p->g)) return 0;
+    const bool linked = p->link.peer_u[0] || p->link.peer_u[1];
+    const int nx = p->g.X1 - p->g.X0;
+    const long long npts = (long long)nx * (p->g.Y1 - p->g.Y0) * (p->g.Z1 - p->g.Z0);
+    if (p->opt_kernel == 0 && npts < 1400000 && !linked) return 0;  // small grids run the generic kernel
+    if (linked && nx < 4 * kSlabEdgePlanes) return 0;
+    // a source that touches a halo cell is scattered after Section0; the second step of a pass could not see it
+    if (p->src_halo_global && p->src_size0 > 0) return 0;
+    FDTD_CHECK(cudaSetDevice(p->dev));
+    if (p->shell_state == 0) {
+        // two-step passes move ring levels between device levels, so all levels must share one halo shell
+        // (Section0 never writes the shell; ghost planes of neighbour slabs are not part of it)
+        Grid box = p->g;
+        if (p->link.peer_u[0]) box.X0 -= FDTD_HALO;
+        if (p->link.peer_u[1]) box.X1 += FDTD_HALO;
+        int *flag = p->d_flags + 8;
+        int rc = launch_shell_check(p->d_u, box, flag, p->stream);
+        if (rc) return rc;
+        int differ = 0;
+        FDTD_CHECK(cudaMemcpyAsync(&differ, flag, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
+        FDTD_CHECK(cudaStreamSynchronize(p->stream));
+        if (!differ) {
+            rc = launch_shell_copy(p->d_u, box, 0, p->work, p->stream);  // placement is the identity here (fresh upload)
+            if (rc) return rc;
+        }
+        p->shell_state = differ ? 2 : 1;
+    }
+    if (p->shell_state == 1) *out = 2;
+    return 0;
+}
+
+extern "C" int fdtd_b200_plan_probe_fuse(fdtd_b200_plan *p, int *t_fuse)
+{
+    if (!p || !t_fuse) return (int)cudaErrorInvalidValue;
+    return plan_fuse_feasible(p, t_fuse);
 }
 
 // Per-slab bookkeeping of one run.
@@ -562,13 +726,32 @@ static int plan_prepare(fdtd_b200_plan *p)
     const bool linked = p->link.peer_u[0] || p->link.peer_u[1];
     if (want == 0) want = (can_tma && (npts >= 1400000 || linked)) ? 2 : 1;
     if (want == 2 && !can_tma) return (int)cudaErrorInvalidValue;
+    if ((p->link.peer_u[0] || p->link.peer_u[1]) && want != 2) return (int)cudaErrorNotSupported;  // slabs need the streaming kernel
+    p->kernel_used = want;
+    // two time steps per pass: a lone slab decides for itself, linked slabs use the depth they agreed on
+    p->t_fuse_used = 1;
+    if (want == 2 && p->opt_t_fuse >= 2) {
+        int depth = 1;
+        if (!linked) {
+            int rc = plan_fuse_feasible(p, &depth);
+            if (rc) return rc;
+        } else {
+            depth = p->t_fuse_agreed >= 2 ? 2 : 1;
+        }
+        if (depth == 2 && !p->tb2.valid) {
+            int rc = tb2_plan_build(p->tb2, p->d_u, p->d_m, p->g, p->cfg, p->opt_exact != 0, p->sm_count);
+            if (rc) return rc;
+        }
+        p->t_fuse_used = depth;
+    }
     if (want == 2 && !p->tma.valid) {
         int rc = tma_plan_build(p->tma, p->d_u, p->d_m, p->g, p->cfg, p->opt_exact != 0, p->sm_count);
+        // with two-step passes the tile options describe that kernel; the one-step kernel (used for the steps
+        // that do not pair up) then takes its default tile
+        if (rc && p->t_fuse_used == 2) rc = tma_plan_build(p->tma, p->d_u, p->d_m, p->g, TmaConfig{}, p->opt_exact != 0, p->sm_count);
         if (rc) return rc;
     }
-    p->kernel_used = want;
-    if ((p->link.peer_u[0] || p->link.peer_u[1]) && want != 2) return (int)cudaErrorNotSupported;  // slabs need the streaming kernel
-    if (p->ncells_all > 0) {  // m at every source's base corner (m may have been re-uploaded)
+    if (p->ncells_all > 0 || p->ncells2 > 0) {  // m at every source's base corner (m may have been re-uploaded)
         int rc = launch_gather_mbase(p->d_m, p->d_base_idx, p->d_mbase, p->n_mbase, p->stream);
         if (rc) return rc;
         p->last_launches++;
@@ -582,21 +765,39 @@ static int run_many(fdtd_b200_plan **ps, int n, int time_m, int time_M, struct p
 {
     if (timers) timers->section0 = timers->section1 = 0.0;
     if (time_M < time_m) return 0;
+    if (n > 1) {  // slabs driven by this process: agree on the depth here (one process per GPU: the driver reduces)
+        int agreed = 2;
+        for (int i = 0; i < n; ++i) {
+            int d = 1;
+            int rc = plan_fuse_feasible(ps[i], &d);
+            if (rc) return rc;
+            agreed = std::min(agreed, d);
+        }
+        for (int i = 0; i < n; ++i) ps[i]->t_fuse_agreed = agreed;
+    }
     for (int i = 0; i < n; ++i) {
         int rc = plan_prepare(ps[i]);
         if (rc) return rc;
     }
+    bool fuse2 = true;
+    for (int i = 0; i < n; ++i) fuse2 = fuse2 && ps[i]->t_fuse_used == 2;
+    if (!fuse2)
+        for (int i = 0; i < n; ++i) ps[i]->t_fuse_used = 1;
     const int first_timed = time_m + FDTD_WARMUP_STEPS;  // openacc.cpp:90-92,148
     const int ntimed = time_M >= first_timed ? time_M - first_timed + 1 : 0;
     std::vector<RunState> st(n);
     int rc = 0;
-    for (int time = time_m; time <= time_M && !rc; ++time) {
+    for (int time = time_m; time <= time_M && !rc;) {
+        // a two-step pass must not straddle the untimed/timed boundary, the end of the run, or the end of src
+        const bool two = fuse2 && time + 1 <= time_M && time + 1 != first_timed && same_source_regime(ps[0], time);
         for (int i = 0; i < n && !rc; ++i) {
             fdtd_b200_plan *p = ps[i];
             RunState &r = st[i];
             if (n > 1) cudaSetDevice(p->dev);
-            if (time >= first_timed) {
-                if (!r.e_begin) r.e_begin = r.stamp(p->stream);
+            if (time >= first_timed && !r.e_begin) r.e_begin = r.stamp(p->stream);
+            if (two) {
+                rc = plan_pass2(p, time, time == time_m);
+            } else if (time >= first_timed) {
                 rc = plan_step(p, time, time == time_m, [&](bool begin) {
                     if (begin) r.s1_spans.push_back({r.stamp(p->stream), nullptr});
                     else r.s1_spans.back().second = r.stamp(p->stream);
@@ -605,6 +806,16 @@ static int run_many(fdtd_b200_plan **ps, int n, int time_m, int time_M, struct p
                 rc = plan_step(p, time, time == time_m, [](bool) {});
             }
         }
+        if (!rc && g_debug_sync) {  // FDTD_B200_SYNC=1: find the launch that faults
+            for (int i = 0; i < n && !rc; ++i) {
+                cudaError_t e = cudaStreamSynchronize(ps[i]->stream);
+                if (e != cudaSuccess) {
+                    fprintf(stderr, "[fdtd_b200] time %d (%s pass) slab %d: %s\n", time, two ? "two-step" : "one-step", i, cudaGetErrorString(e));
+                    rc = (int)e;
+                }
+            }
+        }
+        time += two ? 2 : 1;
     }
     for (int i = 0; i < n; ++i) {
         if (n > 1) cudaSetDevice(ps[i]->dev);

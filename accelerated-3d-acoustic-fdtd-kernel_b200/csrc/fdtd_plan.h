@@ -42,12 +42,29 @@ struct fdtd_b200_plan {
     float *d_mbase = nullptr;
     long long *d_base_idx = nullptr;
     int ncells_int = 0, ncells_halo = 0, ncells_all = 0, n_mbase = 0;
+    // for two-step passes: the interior cells plus the cells on the neighbour slabs' two nearest planes (a pass
+    // recomputes those planes), sorted by (X,Y,Z); src_halo_global: some source of the GLOBAL grid touches a halo
+    // cell (every slab computes the same answer, so slabs agree on whether two-step passes are possible)
+    fdtd::SourceCell *d_cells2 = nullptr;
+    int *d_plane_off2 = nullptr;
+    int ncells2 = 0;
+    bool src_halo_global = false;
 
     // options
     int opt_kernel = 0, opt_exact = 1, opt_fuse = 1, opt_graph = 0, opt_t_fuse = 1;
     fdtd::TmaConfig cfg{};
     fdtd::TmaPlan tma{};
+    fdtd::Tb2Plan tb2{};
     int kernel_used = 0;
+    int t_fuse_used = 1;             // time steps per pass of the current run (1 or 2)
+    int t_fuse_agreed = -1;          // linked slabs: depth all slabs agreed on (-1 = not negotiated -> 1)
+
+    // Placement of the ABI's 3-level ring in the FDTD_LEVELS device levels: ring level r lives in device level
+    // phys[r], `work` is the spare one.  A two-step pass writes u^{n+2} into the spare level (it cannot overwrite
+    // u^{n-1} in place: neighbouring tiles still read it) and the two swap roles.  upload/fill reset to identity.
+    int phys[3] = {0, 1, 2};
+    int work = 3;
+    int shell_state = 0;             // 0 = unknown, 1 = halo shells of all device levels identical, 2 = they differ
 
     // x-slab neighbours: flag words live in the tail of the u allocation (one IPC handle covers both)
     int *d_flags = nullptr;          // [0] ready-from-lower, [1] ready-from-upper, [2..3] CTA counters, [4] error

@@ -18,15 +18,15 @@ struct SlabBlob {                  // FDTD_B200_IPC_BYTES = 160
 static_assert(sizeof(SlabBlob) <= FDTD_B200_IPC_BYTES, "blob too large");
 constexpr int kMagic = 0x46445444;  // "FDTD"
 
-// side 0: the neighbour holds the planes below ours and we fill ITS upper ghost planes (its X1, X1+1) and
-// raise ITS ready-from-upper flag [1]; side 1: we fill its lower ghost planes (its X0-2, X0-1), flag [0].
+// side 0: the neighbour holds the planes below ours and we fill ITS upper ghost planes (its X1, X1+1, ..) and
+// raise ITS ready-from-upper flag [1]; side 1: we fill its lower ghost planes (.., its X0-2, X0-1), flag [0].
 int link_to(fdtd_b200_plan *p, int side, float *peer_u, const SlabBlob &b)
 {
     if (b.nyp != p->g.nyp || b.nzp != p->g.nzp) return (int)cudaErrorInvalidValue;
     int *peer_flags = reinterpret_cast<int *>(reinterpret_cast<char *>(peer_u) + b.flags_offset);
     p->link.peer_u[side] = peer_u;
     p->link.peer_lvl[side] = b.lvl;
-    p->link.peer_plane[side] = side == 0 ? b.X1 : b.X0 - 2;
+    p->link.peer_edge[side] = side == 0 ? b.X1 : b.X0;
     p->link.peer_flag[side] = peer_flags + (side == 0 ? 1 : 0);
     return 0;
 }

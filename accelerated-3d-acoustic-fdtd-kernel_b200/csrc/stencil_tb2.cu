@@ -1,0 +1,445 @@
+// stencil_tb2.cu -- temporal blocking: TWO leapfrog steps per pass (t_fuse = 2), sm_100a.
+//
+// One pass reads u^{n-1}, u^n and m once and writes u^{n+1} and u^{n+2}: ~20-24 B per point per two
+// steps instead of 2 x 16 B -- below the single-step compulsory floor.  No reference kernel does this
+// (the "temporal blocking" comment in cuda_optimized.cu:52-55 is x look-ahead).
+//
+// Structure: overlapped (ghost-zone) tiles in (y,z), streaming in x, both steps in one CTA.
+//   * a CTA owns a TY x TZ output tile and computes step 1 (u^{n+1}) on the tile extended by 2 rows and
+//     one float4 column on every side (ER x EC float4 columns = one consumer thread each), step 2 (u^{n+2})
+//     on the tile itself, two planes behind step 1;
+//   * TMA + mbarrier ring exactly as in stencil_tma.cu: u^n tiles with a radius-4 halo, u^{n-1} and m on the
+//     extended tile, one producer thread, `done[]` barriers (one arrive per warp and iteration) free the slots;
+//   * a thread keeps its own column of u^n (5 planes) AND of its step-1 results (5 planes) in registers, so
+//     step 2 takes its x neighbours, its centre and its "previous" value (u^n) from registers; only the
+//     y/z neighbours of the step-1 plane come from a 6-slot shared-memory ring that the CTA's threads fill
+//     (STS + one mbarrier arrive per warp); the consumer of a plane runs two iterations behind its producer,
+//     so nobody waits in the steady state and no __syncthreads exists;
+//   * points outside the interior box keep their halo value: the host only selects this kernel when the
+//     halo shells of all levels are bit-identical (launch_shell_check) and no source cell lies in a halo;
+//   * sources are injected into BOTH steps in p_src order (every CTA that recomputes a step-1 cell in its
+//     ghost zone injects it too), with the src rows of step n and n+1.
+// Arithmetic: the same point<EXACT>() as the single-step kernels => a two-step pass is BIT-IDENTICAL to two
+// single-step contracted launches (tests/test_tb2_gpu.py).
+#include "fdtd_arith.cuh"
+#include "fdtd_kernels.cuh"
+#include "tma_ptx.cuh"
+
+#include <math.h>
+
+namespace fdtd {
+
+struct Tb2Args {
+    alignas(64) CUtensorMap map_cur;
+    alignas(64) CUtensorMap map_prev;
+    alignas(64) CUtensorMap map_m;
+    Tb2Step s;
+    int tiles_z, tiles_y, xchunk;
+    int edge;  // > 0: the first and last chunk are `edge` planes long (slabs with neighbours)
+};
+
+template <int ER, int EC>
+struct Tb2Shape {
+    static constexpr int TY = ER - 4, TZ = 4 * EC - 8;  // output tile
+    static constexpr int NCA = ER * EC;                 // active consumer threads = extended-tile float4 columns
+    static constexpr int NC = (NCA + 31) / 32 * 32;
+    static constexpr int NCW = NC / 32;
+    static constexpr int NT = NC + 32;                  // + producer warp
+    static constexpr int HP = 4 * EC;                   // pitch of every slot (floats)
+    static constexpr int SU = 5, SP = 3, SM = 5, SB = 6, ND = 8;  // ring depths: u^n, u^{n-1}, m, step-1 planes, done[]
+    static constexpr int UBYTES = (ER + 4) * HP * 4;
+    static constexpr int USLOT = (UBYTES + 127) / 128 * 128;
+    static constexpr int CBYTES = ER * HP * 4;
+    static constexpr int CSLOT = (CBYTES + 127) / 128 * 128;
+    static constexpr int PAD = 128;  // guard before the first ring: column 0 reads two floats to its left
+    static constexpr int SMEM = PAD + SU * USLOT + (SP + SM + SB) * CSLOT + (SU + ND + SB + 1) * 8 + 128;
+    static_assert(NT <= 1024, "too many threads");
+    static_assert(SMEM <= 232448, "shared memory of one CTA exceeds 227 KB");
+};
+
+// Source cells of one plane that fall into this thread's float4: add their contributions in p_src order.
+__device__ __forceinline__ void inject_plane(float4 &r, int X, int Y, int Z, const SourceView &sv)
+{
+    const int c0 = sv.plane_off[X], c1 = sv.plane_off[X + 1];
+    for (int q = c0; q < c1; ++q) {
+        const SourceCell cell = sv.cells[q];
+        const int dzc = cell.Z - Z;
+        if (cell.Y == Y && dzc >= 0 && dzc < 4) {
+            float v = dzc == 0 ? r.x : dzc == 1 ? r.y : dzc == 2 ? r.z : r.w;
+            v = apply_cell(v, cell, sv);
+            r.x = dzc == 0 ? v : r.x;
+            r.y = dzc == 1 ? v : r.y;
+            r.z = dzc == 2 ? v : r.z;
+            r.w = dzc == 3 ? v : r.w;
+        }
+    }
+}
+
+template <int ER, int EC, bool EXACT>
+__global__ void __launch_bounds__(Tb2Shape<ER, EC>::NT, 1) stencil_tb2_kernel(const __grid_constant__ Tb2Args a)
+{
+    using T = Tb2Shape<ER, EC>;
+    constexpr int SU = T::SU, SP = T::SP, SM = T::SM, SB = T::SB, ND = T::ND, HP = T::HP;
+    constexpr int USLOT_F = T::USLOT / 4, CSLOT_F = T::CSLOT / 4;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    float *sU = reinterpret_cast<float *>(smem + T::PAD);
+    float *sP = sU + SU * USLOT_F;
+    float *sM = sP + SP * CSLOT_F;
+    float *sB = sM + SM * CSLOT_F;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sB + SB * CSLOT_F);
+    const uint32_t full0 = smem_u32(bars), done0 = smem_u32(bars + SU), bfull0 = smem_u32(bars + SU + ND);
+    const uint32_t pro0 = smem_u32(bars + SU + ND + SB);  // prologue done: stages 0 and 1 have been read
+
+    const Grid &g = a.s.g;
+    const SlabLink &lk = a.s.link;
+    const int tz = blockIdx.x % a.tiles_z, ty = blockIdx.x / a.tiles_z;
+    // chunk order and the short boundary chunks: as in stencil_tma.cu
+    const int nch = gridDim.y, by = blockIdx.y;
+    const int chunk = by == 0 ? 0 : (by == 1 ? nch - 1 : by - 1);
+    int Xa, Xb;
+    if (a.edge == 0) {
+        Xa = g.X0 + chunk * a.xchunk;
+        Xb = min(g.X1, Xa + a.xchunk);
+    } else if (chunk == 0) {
+        Xa = g.X0;
+        Xb = g.X0 + a.edge;
+    } else if (chunk == nch - 1) {
+        Xa = g.X1 - a.edge;
+        Xb = g.X1;
+    } else {
+        Xa = g.X0 + a.edge + (chunk - 1) * a.xchunk;
+        Xb = min(g.X1 - a.edge, Xa + a.xchunk);
+    }
+    const int np = Xb - Xa;
+    const int Yt = g.Y0 + ty * T::TY, Zt = g.Z0 + tz * T::TZ;  // padded origin of the OUTPUT tile
+    // step 1 is computed on [XC0, XC1): the slab's planes plus, towards a neighbour slab, its two nearest planes
+    // (their u^n, u^{n-1} and m sit in this slab's ghost planes); towards a physical boundary the halo is kept
+    const int XC0 = g.X0 - (lk.peer_u[0] ? 2 : 0), XC1 = g.X1 + (lk.peer_u[1] ? 2 : 0);
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < SU; ++i) mbar_init(full0 + 8 * i, 1);
+        for (int i = 0; i < ND; ++i) mbar_init(done0 + 8 * i, T::NCW);
+        for (int i = 0; i < SB; ++i) mbar_init(bfull0 + 8 * i, T::NCW);
+        mbar_init(pro0, T::NCW);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const int nit = np + 4;  // step-1 iterations: planes Xa-2 .. Xb+1
+    if (threadIdx.x >= T::NC) {
+        // ------------------------------------------------------------------ producer (one thread)
+        // stage s: u^n plane Xa-4+s; for s >= 4 also u^{n-1} and m plane Xa-6+s (= step-1 plane of iteration s-4)
+        if (threadIdx.x == T::NC) {
+            const int nst = nit + 4;
+            int us = 0, ps = 0, ms = 0;
+            bool waited[2] = {!(lk.wait && lk.peer_u[0]), !(lk.wait && lk.peer_u[1])};
+            for (int s = 0; s < nst; ++s) {
+                const int Xp = Xa - 4 + s;  // ghost planes (outside [X0, X1)) are written by the neighbours' previous pass
+                const int side = Xp < g.X0 ? 0 : (Xp >= g.X1 ? 1 : -1);
+                if (side >= 0 && !waited[side]) {
+                    wait_flag(lk.my_flag[side], lk.epoch - 1, lk.err);
+                    waited[side] = true;
+                }
+                // slot reuse: stage s overwrites u^n stage s-5 (last read as the centre plane of iteration s-7), and the
+                // u^{n-1} / m slots of iterations s-7 / s-9.  Stages 5 and 6 overwrite stages 0 and 1, which only the
+                // prologue reads.  (Re-arming a full barrier whose previous phase is still pending is undefined.)
+                if (s == 5) mbar_wait(pro0, 0);
+                if (s >= 7) mbar_wait(done0 + 8 * ((s - 7) % ND), ((s - 7) / ND) & 1);
+                const uint32_t bar = full0 + 8 * us;
+                const bool ctr = s >= 4;
+                mbar_expect_tx(bar, T::UBYTES + (ctr ? 2 * T::CBYTES : 0));
+                tma_load_4d(smem_u32(sU) + us * T::USLOT, &a.map_cur, bar, Zt - 4, Yt - 4, Xp, a.s.l_cur);
+                if (ctr) {
+                    tma_load_4d(smem_u32(sP) + ps * T::CSLOT, &a.map_prev, bar, Zt - 4, Yt - 2, Xp - 2, a.s.l_prev);
+                    tma_load_3d(smem_u32(sM) + ms * T::CSLOT, &a.map_m, bar, Zt - 4, Yt - 2, Xp - 2);
+                    if (++ps == SP) ps = 0;
+                    if (++ms == SM) ms = 0;
+                }
+                if (++us == SU) us = 0;
+            }
+        }
+        return;
+    }
+
+    // ---------------------------------------------------------------------- consumers
+    const bool active = threadIdx.x < T::NCA;
+    const int er = active ? threadIdx.x / EC : 0, ec = active ? threadIdx.x % EC : 0;
+    const int lane = threadIdx.x & 31;
+    const int Y = Yt - 2 + er, Z = Zt - 4 + 4 * ec;
+    const bool inb = active && Y >= g.Y0 && Y < g.Y1 && Z >= g.Z0 && Z < g.Z1;   // interior in (y,z): whole float4
+    const bool core = inb && er >= 2 && er < ER - 2 && ec >= 1 && ec < EC - 1;     // column of the output tile
+    const int ownU = (er + 2) * HP + 4 * ec;  // own column in a u^n slot (rows start at Yt-4)
+    const int ownC = er * HP + 4 * ec;        // own column in a u^{n-1} / m / step-1 slot (rows start at Yt-2)
+
+    const SourceView &sv = a.s.sv;
+    bool chunk_has_src = false;
+    if (sv.ncells > 0) chunk_has_src = (sv.plane_off[min(Xb + 2, g.nxp)] - sv.plane_off[max(Xa - 2, 0)]) > 0;
+    SourceView sv2 = sv;
+    sv2.src_row = a.s.src_row2;
+
+    const long long plane = (long long)g.nyp * g.nzp;
+    const long long row0 = (long long)Y * g.nzp + Z;
+    float *__restrict__ out1 = a.s.u + (long long)a.s.l_n1 * g.lvl + row0;  // + X*plane
+    float *__restrict__ out2 = a.s.u + (long long)a.s.l_n2 * g.lvl + row0;
+    // boundary planes also go to the neighbours' ghost planes (peer stores over NVLink): the two outermost
+    // planes of u^{n+1} and the four outermost planes of u^{n+2}
+    const bool cta_lo = lk.peer_u[0] != nullptr && Xa < g.X0 + 4;
+    const bool cta_hi = lk.peer_u[1] != nullptr && Xb > g.X1 - 4;
+
+    // register queues: qU[s % 5] = own column of u^n, stage s (plane Xa-4+s); qR[i % 5] = own step-1 result of
+    // iteration i (plane Xa-2+i).  The loop is unrolled by 5 so every index is a compile-time constant.
+    float4 qU[5], qR[5];
+#pragma unroll
+    for (int s = 0; s < 5; ++s) qR[s] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        mbar_wait(full0 + 8 * s, 0);
+        qU[s] = lds128(sU + s * USLOT_F + ownU);
+        if (s == 1) {  // stages 0 and 1 are never a centre plane: release them now
+            __syncwarp();
+            if (lane == 0) mbar_arrive(pro0);
+        }
+    }
+
+    int p3 = 0, b6 = 0, d8 = 0;   // i % 3, i % 6, i % 8
+    int b6c = SB - 2;              // (i - 2) % 6
+    uint32_t bpar_c = 1;           // parity of (i-2)/6, valid from i >= 2 (becomes 0 when b6c wraps to 0)
+    for (int i0 = 0; i0 < nit; i0 += 5) {
+        const uint32_t par = (uint32_t)(i0 / 5) & 1u;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            const int i = i0 + k;
+            if (i >= nit) break;
+            // ---------------- step 1: u^{n+1} on plane P1 = Xa-2+i, extended tile
+            const int fsl = (k + 4) % 5, csl = (k + 2) % 5;
+            mbar_wait(full0 + 8 * fsl, par ^ (uint32_t)((k + 4) / 5));
+            qU[fsl] = lds128(sU + fsl * USLOT_F + ownU);
+            const int P1 = Xa - 2 + i;
+            float4 r = qU[csl];  // halo cells keep their value (identical in every level by construction)
+            if (inb && P1 >= XC0 && P1 < XC1) {
+                const float *P = sU + csl * USLOT_F + ownU;
+                const float4 ym2 = lds128(P - 2 * HP), ym1 = lds128(P - HP), yp1 = lds128(P + HP), yp2 = lds128(P + 2 * HP);
+                const float2 zl = lds64(P - 2), zr = lds64(P + 4);
+                const float4 pv = lds128(sP + p3 * CSLOT_F + ownC);
+                const float4 mv = lds128(sM + k * CSLOT_F + ownC);  // m slot (s-4) % 5 = i % 5 = k
+                const float4 c = r, xm2 = qU[k % 5], xm1 = qU[(k + 1) % 5], xp1 = qU[(k + 3) % 5], xp2 = qU[fsl];
+                r.x = point<EXACT>(c.x, xm2.x, xm1.x, xp1.x, xp2.x, ym2.x, ym1.x, yp1.x, yp2.x, zl.x, zl.y, c.y, c.z, pv.x, mv.x, a.s.k);
+                r.y = point<EXACT>(c.y, xm2.y, xm1.y, xp1.y, xp2.y, ym2.y, ym1.y, yp1.y, yp2.y, zl.y, c.x, c.z, c.w, pv.y, mv.y, a.s.k);
+                r.z = point<EXACT>(c.z, xm2.z, xm1.z, xp1.z, xp2.z, ym2.z, ym1.z, yp1.z, yp2.z, c.x, c.y, c.w, zr.x, pv.z, mv.z, a.s.k);
+                r.w = point<EXACT>(c.w, xm2.w, xm1.w, xp1.w, xp2.w, ym2.w, ym1.w, yp1.w, yp2.w, c.y, c.z, zr.x, zr.y, pv.w, mv.w, a.s.k);
+                if (chunk_has_src) inject_plane(r, P1, Y, Z, sv);  // rare: source cells of step n (also in the ghost zone)
+                if (core && P1 >= Xa && P1 < Xb) {
+                    *reinterpret_cast<float4 *>(out1 + (long long)P1 * plane) = r;
+                    if (cta_lo && P1 < g.X0 + 2)
+                        *reinterpret_cast<float4 *>(lk.peer_u[0] + a.s.l_n1 * lk.peer_lvl[0] + (long long)(lk.peer_edge[0] + P1 - g.X0) * plane + row0) = r;
+                    if (cta_hi && P1 >= g.X1 - 2)
+                        *reinterpret_cast<float4 *>(lk.peer_u[1] + a.s.l_n1 * lk.peer_lvl[1] + (long long)(lk.peer_edge[1] + P1 - g.X1) * plane + row0) = r;
+                }
+            }
+            qR[k % 5] = r;
+            if (active) *reinterpret_cast<float4 *>(sB + b6 * CSLOT_F + ownC) = r;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bfull0 + 8 * b6);
+
+            // ---------------- step 2: u^{n+2} on plane X = Xa+i-4 (centre = step-1 plane of iteration i-2)
+            if (i >= 4) {
+                mbar_wait(bfull0 + 8 * b6c, bpar_c);
+                if (core) {
+                    const int X = Xa + i - 4;
+                    const float *P = sB + b6c * CSLOT_F + ownC;
+                    const float4 ym2 = lds128(P - 2 * HP), ym1 = lds128(P - HP), yp1 = lds128(P + HP), yp2 = lds128(P + 2 * HP);
+                    const float2 zl = lds64(P - 2), zr = lds64(P + 4);
+                    const float4 mv = lds128(sM + ((k + 3) % 5) * CSLOT_F + ownC);  // m of plane X: slot (i-2) % 5
+                    const float4 c = qR[(k + 3) % 5], xm2 = qR[(k + 1) % 5], xm1 = qR[(k + 2) % 5], xp1 = qR[(k + 4) % 5], xp2 = qR[k % 5];
+                    const float4 pv = qU[k % 5];  // u^n on plane X (stage i): the "previous" level of step 2
+                    float4 o;
+                    o.x = point<EXACT>(c.x, xm2.x, xm1.x, xp1.x, xp2.x, ym2.x, ym1.x, yp1.x, yp2.x, zl.x, zl.y, c.y, c.z, pv.x, mv.x, a.s.k);
+                    o.y = point<EXACT>(c.y, xm2.y, xm1.y, xp1.y, xp2.y, ym2.y, ym1.y, yp1.y, yp2.y, zl.y, c.x, c.z, c.w, pv.y, mv.y, a.s.k);
+                    o.z = point<EXACT>(c.z, xm2.z, xm1.z, xp1.z, xp2.z, ym2.z, ym1.z, yp1.z, yp2.z, c.x, c.y, c.w, zr.x, pv.z, mv.z, a.s.k);
+                    o.w = point<EXACT>(c.w, xm2.w, xm1.w, xp1.w, xp2.w, ym2.w, ym1.w, yp1.w, yp2.w, c.y, c.z, zr.x, zr.y, pv.w, mv.w, a.s.k);
+                    if (chunk_has_src) inject_plane(o, X, Y, Z, sv2);  // source cells of step n+1
+                    *reinterpret_cast<float4 *>(out2 + (long long)X * plane) = o;
+                    if (cta_lo && X < g.X0 + 4)
+                        *reinterpret_cast<float4 *>(lk.peer_u[0] + a.s.l_n2 * lk.peer_lvl[0] + (long long)(lk.peer_edge[0] + X - g.X0) * plane + row0) = o;
+                    if (cta_hi && X >= g.X1 - 4)
+                        *reinterpret_cast<float4 *>(lk.peer_u[1] + a.s.l_n2 * lk.peer_lvl[1] + (long long)(lk.peer_edge[1] + X - g.X1) * plane + row0) = o;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(done0 + 8 * d8);  // iteration i done: u^n stage i+2, u^{n-1} and m slots reusable
+
+            if (++p3 == SP) p3 = 0;
+            if (++b6 == SB) b6 = 0;
+            if (++d8 == ND) d8 = 0;
+            if (++b6c == SB) {
+                b6c = 0;
+                bpar_c ^= 1;
+            }
+        }
+    }
+
+    if (cta_lo || cta_hi) {
+        // every consumer thread of this CTA has issued its peer stores: count the CTA, and let the last CTA of
+        // a boundary publish the pass's epoch in the neighbour's flag (same protocol as stencil_tma.cu)
+        asm volatile("bar.sync 1, %0;" ::"r"(T::NC) : "memory");
+        if (threadIdx.x == 0) {
+            __threadfence_system();
+#pragma unroll
+            for (int side = 0; side < 2; ++side) {
+                if (!(side == 0 ? cta_lo : cta_hi)) continue;
+                const int done = atomicAdd(lk.counter + side, 1);
+                if (done == lk.expect[side] - 1) {
+                    atomicExch(lk.counter + side, 0);
+                    __threadfence_system();
+                    raise_flag(lk.peer_flag[side], lk.epoch);
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------- halo-shell check / copy
+// The shell = every padded cell outside the box [X0,X1) x [Y0,Y1) x [Z0,Z1).  Section0 never writes it, so it
+// is constant in time; a two-step pass moves ring levels between physical levels and therefore needs the
+// shells of all levels to be the same.  One (x,y) row per threadIdx.y, z strided over threadIdx.x.
+// check: *flag |= 1 if the shells of levels 0, 1 and 2 differ anywhere (bit compare).
+// copy : shell of level `from` -> level `to`.
+template <bool COPY>
+__global__ void shell_kernel(float *__restrict__ u, Grid g, int from, int to, int *flag)
+{
+    const long long row = (long long)blockIdx.x * blockDim.y + threadIdx.y;
+    if (row >= (long long)g.nxp * g.nyp) return;
+    const int X = (int)(row / g.nyp), Y = (int)(row % g.nyp);
+    const bool whole = X < g.X0 || X >= g.X1 || Y < g.Y0 || Y >= g.Y1;
+    unsigned *a = reinterpret_cast<unsigned *>(u) + row * g.nzp;
+    bool bad = false;
+    for (int z = threadIdx.x; z < g.nzp; z += blockDim.x) {
+        if (!whole && z >= g.Z0 && z < g.Z1) continue;
+        if (COPY) {
+            a[(long long)to * g.lvl + z] = a[(long long)from * g.lvl + z];
+        } else {
+            const unsigned v = a[z];
+            bad |= (v != a[g.lvl + z]) || (v != a[2 * g.lvl + z]);
+        }
+    }
+    if (!COPY && bad) atomicOr(flag, 1);
+}
+
+int launch_shell_check(float *u, const Grid &g, int *flag, cudaStream_t stream)
+{
+    cudaError_t e = cudaMemsetAsync(flag, 0, sizeof(int), stream);
+    if (e != cudaSuccess) return (int)e;
+    dim3 block(32, 8);
+    const long long rows = (long long)g.nxp * g.nyp;
+    shell_kernel<false><<<(unsigned)((rows + block.y - 1) / block.y), block, 0, stream>>>(u, g, 0, 0, flag);
+    return (int)cudaGetLastError();
+}
+
+int launch_shell_copy(float *u, const Grid &g, int from, int to, cudaStream_t stream)
+{
+    dim3 block(32, 8);
+    const long long rows = (long long)g.nxp * g.nyp;
+    shell_kernel<true><<<(unsigned)((rows + block.y - 1) / block.y), block, 0, stream>>>(u, g, from, to, nullptr);
+    return (int)cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------- host side
+typedef void (*Tb2KernelFn)(const Tb2Args);
+struct Tb2Variant {
+    int er, ec;
+    bool exact;
+    Tb2KernelFn fn;
+    int nt;
+    size_t smem;
+};
+#define FDTD_TB2_1(ER_, EC_, EX_) {ER_, EC_, EX_, stencil_tb2_kernel<ER_, EC_, EX_>, Tb2Shape<ER_, EC_>::NT, (size_t)Tb2Shape<ER_, EC_>::SMEM}
+#define FDTD_TB2(ER_, EC_) FDTD_TB2_1(ER_, EC_, false), FDTD_TB2_1(ER_, EC_, true)
+static const Tb2Variant g_tb2[] = {
+    // extended tile (rows, float4 columns) -> output tile (ER-4) x (4*EC-8); first match of (ty, tz) wins
+    FDTD_TB2(36, 18),  // 32 x 64
+    FDTD_TB2(32, 18),  // 28 x 64
+    FDTD_TB2(20, 34),  // 16 x 128
+    FDTD_TB2(20, 18),  // 16 x 64
+};
+static const int g_ntb2 = (int)(sizeof(g_tb2) / sizeof(g_tb2[0]));
+
+int tb2_plan_build(Tb2Plan &p, float *u, const float *m, const Grid &g, const TmaConfig &cfg, bool exact, int sm_count)
+{
+    p.valid = false;
+    if (!tma_supported(g)) return (int)cudaErrorInvalidValue;
+    const int ny = g.Y1 - g.Y0, nz = g.Z1 - g.Z0, nx = g.X1 - g.X0;
+    int vi = -1;
+    for (int i = 0; i < g_ntb2 && vi < 0; ++i)
+        if (g_tb2[i].exact == exact && (cfg.ty <= 0 || g_tb2[i].er - 4 == cfg.ty) && (cfg.tz <= 0 || 4 * g_tb2[i].ec - 8 == cfg.tz))
+            vi = i;
+    if (vi < 0) return (int)cudaErrorInvalidValue;
+    const Tb2Variant &v = g_tb2[vi];
+    const int ty = v.er - 4, tz = 4 * v.ec - 8;
+
+    cuuint64_t dims_u[4] = {(cuuint64_t)g.nzp, (cuuint64_t)g.nyp, (cuuint64_t)g.nxp, (cuuint64_t)FDTD_LEVELS};
+    cuuint32_t box_u[4] = {(cuuint32_t)(4 * v.ec), (cuuint32_t)(v.er + 4), 1, 1};
+    cuuint32_t box_c[4] = {(cuuint32_t)(4 * v.ec), (cuuint32_t)v.er, 1, 1};
+    int rc;
+    if ((rc = encode_tensor_map(&p.map_cur, u, 4, dims_u, box_u))) return rc;
+    if ((rc = encode_tensor_map(&p.map_prev, u, 4, dims_u, box_c))) return rc;
+    if ((rc = encode_tensor_map(&p.map_m, m, 3, dims_u, box_c))) return rc;
+    cudaError_t e = cudaFuncSetAttribute((const void *)v.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v.smem);
+    if (e != cudaSuccess) return (int)e;
+
+    // x chunking: one CTA per SM; several full waves, chunks long enough to amortise the 8-plane prologue
+    const int tiles = ((ny + ty - 1) / ty) * ((nz + tz - 1) / tz);
+    int xchunk = cfg.xchunk;
+    if (xchunk <= 0) {
+        double best = -1.0;
+        for (int nch = 1; nch <= nx; ++nch) {
+            const int xc = (nx + nch - 1) / nch;
+            if (xc < 16 && nch > 1) break;
+            if ((nx + xc - 1) / xc != nch) continue;
+            const double waves = tiles * (double)nch / sm_count, full = ceil(waves);
+            const double eff = waves / full * full / (full + 0.25) * xc / (xc + 8.0);
+            if (eff > best) {
+                best = eff;
+                xchunk = xc;
+            }
+        }
+    }
+    p.ty = ty;
+    p.tz = tz;
+    p.xchunk = xchunk;
+    p.variant = vi;
+    p.smem_bytes = v.smem;
+    p.valid = true;
+    return 0;
+}
+
+int launch_stencil_tb2(const Tb2Plan &p, const Tb2Step &a, bool exact, cudaStream_t stream)
+{
+    if (!p.valid) return (int)cudaErrorInvalidValue;
+    const Tb2Variant &v = g_tb2[p.variant];
+    if (v.exact != exact) return (int)cudaErrorInvalidValue;
+    const int ny = a.g.Y1 - a.g.Y0, nz = a.g.Z1 - a.g.Z0, nx = a.g.X1 - a.g.X0;
+    if (nx <= 0) return 0;
+    Tb2Args args;
+    args.map_cur = p.map_cur;
+    args.map_prev = p.map_prev;
+    args.map_m = p.map_m;
+    args.s = a;
+    args.tiles_z = (nz + p.tz - 1) / p.tz;
+    args.tiles_y = (ny + p.ty - 1) / p.ty;
+    args.xchunk = p.xchunk;
+    args.edge = 0;
+    int nchunks = (nx + p.xchunk - 1) / p.xchunk;
+    const bool linked = a.link.peer_u[0] != nullptr || a.link.peer_u[1] != nullptr;
+    if (linked) {  // short boundary chunks hold the 4 planes a neighbour needs; the usual chunks lie in between
+        if (nx < 4 * kSlabEdgePlanes) return (int)cudaErrorInvalidValue;
+        args.edge = kSlabEdgePlanes;
+        nchunks = 2 + (nx - 2 * kSlabEdgePlanes + p.xchunk - 1) / p.xchunk;
+        args.s.link.expect[0] = args.s.link.expect[1] = args.tiles_z * args.tiles_y;
+    }
+    dim3 grid(args.tiles_z * args.tiles_y, nchunks, 1);
+    if (grid.y > 65535) return (int)cudaErrorInvalidValue;
+    v.fn<<<grid, v.nt, v.smem, stream>>>(args);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace fdtd

@@ -21,6 +21,7 @@
 // slot j%(S0-2) become free together, so one empty barrier per halo slot suffices).
 #include "fdtd_arith.cuh"
 #include "fdtd_kernels.cuh"
+#include "tma_ptx.cuh"
 
 #include <cudaTypedefs.h>
 #include <math.h>
@@ -34,75 +35,8 @@ struct TmaArgs {
     alignas(64) CUtensorMap map_m;
     StepArgs s;
     int tiles_z, tiles_y, xchunk;
+    int edge;  // > 0: the first and last chunk are only `edge` planes long (slabs with neighbours)
 };
-
-// ---------------------------------------------------------------------------- PTX helpers
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
-{
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra WAIT_DONE;\n"
-        "bra WAIT_LOOP;\n"
-        "WAIT_DONE:\n"
-        "}\n" ::"r"(bar),
-        "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1,
-                                            int c2, int c3)
-{
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-        ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1,
-                                            int c2)
-{
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-        ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
-        : "memory");
-}
-// Spin (bounded) until *flag >= want; the neighbour stores the flag with release.sys after its
-// boundary planes have landed in this GPU's memory.  On timeout mark *err and carry on.
-__device__ __forceinline__ void wait_flag(const int *flag, int want, int *err)
-{
-    int v, tries = 0;
-    for (;;) {
-        asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
-        if (v >= want) break;
-        __nanosleep(200);
-        if (++tries > 5000000) {  // > 1 s: the neighbour is gone
-            atomicExch(err, 1);
-            break;
-        }
-    }
-    asm volatile("fence.proxy.async;" ::: "memory");  // the ghost planes are read by TMA (async proxy)
-}
-__device__ __forceinline__ void raise_flag(int *flag, int value)
-{
-    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(flag), "r"(value) : "memory");
-}
-__device__ __forceinline__ float4 lds128(const float *p) { return *reinterpret_cast<const float4 *>(p); }
-__device__ __forceinline__ float2 lds64(const float *p) { return *reinterpret_cast<const float2 *>(p); }
 
 // ---------------------------------------------------------------------------- geometry of one variant
 // S0_ = halo-plane ring depth; the plane loop is unrolled by S0_ and the register queue has period 5,
@@ -152,8 +86,20 @@ __global__ void __launch_bounds__(TileShape<TY, TZ, RY, NS>::NT, MINB)
     // neighbours' ghost planes are written (and their flags raised) early in the step
     const int nch = gridDim.y, by = blockIdx.y;
     const int chunk = by == 0 ? 0 : (by == 1 ? nch - 1 : by - 1);
-    const int Xa = g.X0 + chunk * a.xchunk;
-    const int Xb = min(g.X1, Xa + a.xchunk);
+    int Xa, Xb;
+    if (a.edge == 0) {
+        Xa = g.X0 + chunk * a.xchunk;
+        Xb = min(g.X1, Xa + a.xchunk);
+    } else if (chunk == 0) {       // short boundary chunks: the neighbours get their ghost planes (and flags)
+        Xa = g.X0;                  // within the first wave of CTAs instead of after a full-length chunk
+        Xb = g.X0 + a.edge;
+    } else if (chunk == nch - 1) {
+        Xa = g.X1 - a.edge;
+        Xb = g.X1;
+    } else {
+        Xa = g.X0 + a.edge + (chunk - 1) * a.xchunk;
+        Xb = min(g.X1 - a.edge, Xa + a.xchunk);
+    }
     const int np = Xb - Xa;         // output planes of this CTA (>= 1 by construction)
     const SlabLink &lk = a.s.link;
     const int Yt = g.Y0 + ty * TY;  // padded origin of the tile
@@ -231,8 +177,8 @@ __global__ void __launch_bounds__(TileShape<TY, TZ, RY, NS>::NT, MINB)
     }
 
     // boundary planes also go to the neighbours' ghost planes (peer stores over NVLink)
-    const bool cta_lo = lk.peer_u[0] != nullptr && Xa < g.X0 + 2;
-    const bool cta_hi = lk.peer_u[1] != nullptr && Xb > g.X1 - 2;
+    const bool cta_lo = lk.peer_u[0] != nullptr && Xa < g.X0 + lk.depth;
+    const bool cta_hi = lk.peer_u[1] != nullptr && Xb > g.X1 - lk.depth;
     const long long row0 = (long long)Y * g.nzp + Z;
 
     int ms = 0;  // centre-ring slot j % S1
@@ -314,14 +260,14 @@ __global__ void __launch_bounds__(TileShape<TY, TZ, RY, NS>::NT, MINB)
             out += plane;
             if (cta_lo || cta_hi) {
                 const int X = Xa + j;
-                if (cta_lo && X < g.X0 + 2) {
-                    float *dst = lk.peer_u[0] + a.s.t2 * lk.peer_lvl[0] + (long long)(lk.peer_plane[0] + X - g.X0) * plane + row0;
+                if (cta_lo && X < g.X0 + lk.depth) {
+                    float *dst = lk.peer_u[0] + a.s.t2 * lk.peer_lvl[0] + (long long)(lk.peer_edge[0] + X - g.X0) * plane + row0;
 #pragma unroll
                     for (int r = 0; r < RY; ++r)
                         if (z_ok && Y + r < g.Y1) *reinterpret_cast<float4 *>(dst + (long long)r * g.nzp) = o[r];
                 }
-                if (cta_hi && X >= g.X1 - 2) {
-                    float *dst = lk.peer_u[1] + a.s.t2 * lk.peer_lvl[1] + (long long)(lk.peer_plane[1] + X - (g.X1 - 2)) * plane + row0;
+                if (cta_hi && X >= g.X1 - lk.depth) {
+                    float *dst = lk.peer_u[1] + a.s.t2 * lk.peer_lvl[1] + (long long)(lk.peer_edge[1] + X - g.X1) * plane + row0;
 #pragma unroll
                     for (int r = 0; r < RY; ++r)
                         if (z_ok && Y + r < g.Y1) *reinterpret_cast<float4 *>(dst + (long long)r * g.nzp) = o[r];
@@ -401,7 +347,7 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode()
     return fn;
 }
 
-static int encode_map(CUtensorMap *map, const float *base, int rank, const cuuint64_t *dims, const cuuint32_t *box)
+int encode_tensor_map(CUtensorMap *map, const float *base, int rank, const cuuint64_t *dims, const cuuint32_t *box)
 {
     PFN_cuTensorMapEncodeTiled_v12000 enc = get_encode();
     if (!enc) return (int)cudaErrorNotSupported;
@@ -442,13 +388,13 @@ int tma_plan_build(TmaPlan &p, float *u, const float *m, const Grid &g, const Tm
     if (vi < 0) return (int)cudaErrorInvalidValue;
     const Variant &v = g_variants[vi];
 
-    cuuint64_t dims_u[4] = {(cuuint64_t)g.nzp, (cuuint64_t)g.nyp, (cuuint64_t)g.nxp, 3};
+    cuuint64_t dims_u[4] = {(cuuint64_t)g.nzp, (cuuint64_t)g.nyp, (cuuint64_t)g.nxp, (cuuint64_t)FDTD_LEVELS};
     cuuint32_t box_h[4] = {(cuuint32_t)(tz + 8), (cuuint32_t)(ty + 4), 1, 1};
     cuuint32_t box_c[4] = {(cuuint32_t)tz, (cuuint32_t)ty, 1, 1};
     int rc;
-    if ((rc = encode_map(&p.map_halo, u, 4, dims_u, box_h))) return rc;
-    if ((rc = encode_map(&p.map_ctr, u, 4, dims_u, box_c))) return rc;
-    if ((rc = encode_map(&p.map_m, m, 3, dims_u, box_c))) return rc;
+    if ((rc = encode_tensor_map(&p.map_halo, u, 4, dims_u, box_h))) return rc;
+    if ((rc = encode_tensor_map(&p.map_ctr, u, 4, dims_u, box_c))) return rc;
+    if ((rc = encode_tensor_map(&p.map_m, m, 3, dims_u, box_c))) return rc;
 
     cudaError_t e = cudaFuncSetAttribute((const void *)v.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v.smem);
     if (e != cudaSuccess) return (int)e;
@@ -508,13 +454,24 @@ int launch_stencil_tma(const TmaPlan &p, const StepArgs &a, bool exact, cudaStre
     args.tiles_z = (nz + p.tz - 1) / p.tz;
     args.tiles_y = (ny + p.ty - 1) / p.ty;
     args.xchunk = p.xchunk;
-    dim3 grid(args.tiles_z * args.tiles_y, (nx + p.xchunk - 1) / p.xchunk, 1);
+    args.edge = 0;
+    int nchunks = (nx + p.xchunk - 1) / p.xchunk;
+    const bool linked = a.link.peer_u[0] != nullptr || a.link.peer_u[1] != nullptr;
+    if (linked && nx >= 4 * kSlabEdgePlanes) {  // short boundary chunks + the usual chunks in between
+        args.edge = kSlabEdgePlanes;
+        nchunks = 2 + (nx - 2 * kSlabEdgePlanes + p.xchunk - 1) / p.xchunk;
+    }
+    dim3 grid(args.tiles_z * args.tiles_y, nchunks, 1);
     if (grid.y > 65535) return (int)cudaErrorInvalidValue;
     // CTAs whose chunk holds one of the two lowest / two highest planes of the slab
-    const int nchunks = (int)grid.y, last_len = nx - (nchunks - 1) * p.xchunk;
     const int tiles = (int)grid.x;
-    args.s.link.expect[0] = tiles * ((p.xchunk >= 2 || nchunks == 1) ? 1 : 2);
-    args.s.link.expect[1] = tiles * ((last_len >= 2 || nchunks == 1) ? 1 : 2);
+    if (args.edge) {
+        args.s.link.expect[0] = args.s.link.expect[1] = tiles;
+    } else {
+        const int last_len = nx - (nchunks - 1) * p.xchunk;
+        args.s.link.expect[0] = tiles * ((p.xchunk >= 2 || nchunks == 1) ? 1 : 2);
+        args.s.link.expect[1] = tiles * ((last_len >= 2 || nchunks == 1) ? 1 : 2);
+    }
     v.fn<<<grid, v.nt, v.smem, stream>>>(args);
     return (int)cudaGetLastError();
 }

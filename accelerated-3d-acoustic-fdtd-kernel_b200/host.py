@@ -95,6 +95,8 @@ def lib():
     L.fdtd_b200_plan_destroy.restype, L.fdtd_b200_plan_destroy.argtypes = i, [vp]
     L.fdtd_b200_plan_u.restype, L.fdtd_b200_plan_u.argtypes = vp, [vp]
     L.fdtd_b200_plan_m.restype, L.fdtd_b200_plan_m.argtypes = vp, [vp]
+    L.fdtd_b200_plan_level.restype, L.fdtd_b200_plan_level.argtypes = vp, [vp, i]
+    L.fdtd_b200_plan_probe_fuse.restype, L.fdtd_b200_plan_probe_fuse.argtypes = i, [vp, C.POINTER(i)]
     L.fdtd_b200_plan_level_elems.restype, L.fdtd_b200_plan_level_elems.argtypes = C.c_size_t, [vp]
     L.fdtd_b200_plan_upload.restype, L.fdtd_b200_plan_upload.argtypes = i, [vp, vp, vp]
     L.fdtd_b200_plan_download.restype, L.fdtd_b200_plan_download.argtypes = i, [vp, vp]
@@ -130,7 +132,7 @@ def exported_symbols():
     return [
         "Kernel_CUDA_Optimized", "Kernel_B200", "FDTD_SetRuntimeConfig",
         "fdtd_b200_plan_create", "fdtd_b200_plan_destroy", "fdtd_b200_plan_u", "fdtd_b200_plan_m",
-        "fdtd_b200_plan_level_elems", "fdtd_b200_plan_upload", "fdtd_b200_plan_download", "fdtd_b200_plan_fill",
+        "fdtd_b200_plan_level", "fdtd_b200_plan_probe_fuse", "fdtd_b200_plan_level_elems", "fdtd_b200_plan_upload", "fdtd_b200_plan_download", "fdtd_b200_plan_fill",
         "fdtd_b200_plan_fill_dense", "fdtd_b200_plan_set_sources", "fdtd_b200_plan_run",
         "fdtd_b200_plan_last_launches", "fdtd_b200_plan_last_kernel_seconds", "fdtd_b200_plan_set_option",
         "fdtd_b200_plan_get_option", "fdtd_b200_plan_ipc_export", "fdtd_b200_plan_ipc_attach",
@@ -282,6 +284,16 @@ class Plan:
     @property
     def m_ptr(self) -> int:
         return lib().fdtd_b200_plan_m(self._h)
+
+    def level_ptr(self, ring_level: int) -> int:
+        """Device pointer of ring level 0..2 (two-step passes rotate a spare device level through the ring)."""
+        return lib().fdtd_b200_plan_level(self._h, ring_level)
+
+    def probe_fuse(self) -> int:
+        """Time steps per pass (1 or 2) this slab could run now; linked slabs must agree on the minimum."""
+        v = C.c_int()
+        _check(lib().fdtd_b200_plan_probe_fuse(self._h, C.byref(v)), "fdtd_b200_plan_probe_fuse")
+        return v.value
 
     @property
     def level_elems(self) -> int:

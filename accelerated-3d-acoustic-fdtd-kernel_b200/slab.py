@@ -70,6 +70,11 @@ class SlabRun:
     def run(self, time_m: int, time_M: int):
         """All ranks advance the same steps.  The barrier makes sure every neighbour's last boundary
         planes have landed (and nobody refills a field a neighbour is still writing ghosts into)."""
+        if self.plan.get_option("t_fuse") >= 2:
+            # two-step passes only if every slab can run them (same pass schedule on all ranks)
+            depths = [None] * self.world
+            self.dist.all_gather_object(depths, self.plan.probe_fuse())
+            self.plan.set_option("t_fuse_agreed", min(depths))
         t = self.plan.run(time_m, time_M)
         self.dist.barrier()
         return t

@@ -98,6 +98,10 @@ int fdtd_b200_plan_destroy(fdtd_b200_plan *plan);
 /* Device pointers of the slab's arrays (for wrapping as torch tensors / IPC export). */
 float *fdtd_b200_plan_u(fdtd_b200_plan *plan);
 float *fdtd_b200_plan_m(fdtd_b200_plan *plan);
+/* Device pointer of ring level 0..2 (u[level] of the reference ABI).  The allocation holds one spare level
+ * beyond the ABI's three; two-step passes rotate it through the ring, so after a run with t_fuse = 2 ring
+ * level r is NOT necessarily at plan_u + r*level_elems -- use this accessor (download does). */
+float *fdtd_b200_plan_level(fdtd_b200_plan *plan, int ring_level);
 size_t fdtd_b200_plan_level_elems(fdtd_b200_plan *plan); /* (nx+8)(ny+8)(nz+8) */
 
 /* Host <-> device staging of whole arrays (either pointer may be NULL to skip it). */
@@ -134,10 +138,22 @@ double fdtd_b200_plan_last_kernel_seconds(fdtd_b200_plan *plan);
  * Options: "kernel" 0 = auto, 1 = generic (any extents), 2 = tma (2.5D x-streaming, TMA ring);
  * "exact" 1 = replay the reference's fp32 operation order (0 ulp vs the host build), 0 = contracted;
  * "fuse_inject" 1 = scatter inside the stencil epilogue; "tile_y","tile_z","rows","xchunk";
- * "graph" 1 = replay the time loop as a CUDA graph; "t_fuse" temporal-blocking depth.
+ * "t_fuse" temporal-blocking depth: 1 = one time step per pass, >= 2 = two time steps per pass (u^{n+1} and
+ * u^{n+2} from one read of u^{n-1}, u^n, m; bit-identical to two one-step passes).  Two-step passes need the
+ * halo shells of the three levels to be identical and no source corner in a halo cell; otherwise, and for the
+ * steps that do not pair up (the untimed/timed boundary, an odd remainder), one-step passes run.
+ * get_option also answers "kernel_used", "t_fuse_used", "tile_y_used", "tile_z_used", "rows_used", "xchunk_used",
+ * "ncells_fused", "ncells_halo" for the last run.
  */
 int fdtd_b200_plan_set_option(fdtd_b200_plan *plan, const char *key, int value);
 int fdtd_b200_plan_get_option(fdtd_b200_plan *plan, const char *key, int *value);
+
+/*
+ * Depth (1 or 2) this slab could run with its current options, sources and field contents.  Linked slabs must
+ * all use the same depth: one process per GPU calls this on every rank, takes the minimum (an all-reduce on
+ * the host side) and sets option "t_fuse_agreed" before the run; fdtd_b200_run_slabs does it internally.
+ */
+int fdtd_b200_plan_probe_fuse(fdtd_b200_plan *plan, int *t_fuse);
 
 /* ---- x-slab neighbours (one process per GPU; handles travel over torch.distributed) */
 #define FDTD_B200_IPC_BYTES 160

@@ -28,14 +28,17 @@ def main():
     ap.add_argument("--exact", type=str, default="1,0")
     ap.add_argument("--tiles", type=str, default="")
     ap.add_argument("--generic", action="store_true")
+    ap.add_argument("--nsrc", type=int, default=1)
+    ap.add_argument("--global-nx", type=int, default=0, help="place the source lattice as if the slab were part of this global grid")
     ap.add_argument("--dense", action="store_true", help="dense sin field instead of the zero field")
+    ap.add_argument("--tfuse", type=int, default=1, help="2: two-step passes (tiles are then the output tiles TYxTZ of stencil_tb2.cu)")
     a = ap.parse_args()
     n, T = a.n, a.steps + 5
     nx, ny, nz = [int(x) for x in a.shape.split(",")] if a.shape else (n, n, n)
     npts = nx * ny * nz
     tiles = TILES if not a.tiles else [tuple(int(x) for x in t.split("x")) for t in a.tiles.split(",")]
-    tiles = [t if len(t) == 4 else t + (5,) for t in tiles]
-    src, crd = pkg.fill_ricker(T, 1), pkg.fill_source_coords(1, nx, ny, nz)
+    tiles = [t + ((1, 5) if len(t) == 2 else (5,) if len(t) == 3 else ()) for t in tiles]
+    src, crd = pkg.fill_ricker(T, a.nsrc), pkg.fill_source_coords(a.nsrc, a.global_nx or nx, ny, nz)
     with pkg.Plan(nx, ny, nz, deviceid=0) as p:
         p.set_sources(src, crd)
         rows = []
@@ -51,7 +54,7 @@ def main():
                                                           [int(x) for x in a.exact.split(",")]):
             p.fill_dense() if a.dense else p.fill(0.0, 1.5)
             for k, v in (("kernel", 2), ("exact", exact), ("tile_y", ty), ("tile_z", tz), ("rows", st), ("stages", ns),
-                         ("xchunk", xc)):
+                         ("xchunk", xc), ("t_fuse", a.tfuse)):
                 p.set_option(k, v)
             try:
                 t = p.run(0, T - 1)
@@ -60,6 +63,8 @@ def main():
                 continue
             g = npts * a.steps / (t.section0 + t.section1) / 1e9
             rows.append((g, ty, tz, st, ns, p.get_option("xchunk_used"), exact))
+            if p.get_option("t_fuse_used") != a.tfuse:
+                print(f"tile {ty}x{tz}: t_fuse {a.tfuse} not honoured", flush=True)
             print(f"tile {ty:3d}x{tz:3d} r{st} s{ns:2d} xchunk {rows[-1][5]:4d} exact={exact}: {g:8.1f} Gpts/s  "
                   f"{16 * g / 6551.7:6.3f} of HBM  ({p.last_kernel_seconds * 1e6:8.1f} us/step)", flush=True)
     rows.sort(reverse=True)

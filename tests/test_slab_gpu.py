@@ -111,7 +111,7 @@ def _free_port():
     return p
 
 
-def _ipc_worker(rank, world, port, shape, T, S, out_path):
+def _ipc_worker(rank, world, port, shape, T, S, out_path, t_fuse=1):
     import importlib
     import sys
 
@@ -124,13 +124,19 @@ def _ipc_worker(rank, world, port, shape, T, S, out_path):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
-    u, m, src, crd = _case(5, shape, T, S, seam_parts=world)
+    if t_fuse == 2:
+        from test_tb2_gpu import fused_case
+        u, m, src, crd = fused_case(5, shape, T, S, seam_parts=world)
+    else:
+        u, m, src, crd = _case(5, shape, T, S, seam_parts=world)
     sr = pkg.SlabRun(dist, shape[0], shape[1], shape[2], rank)
+    sr.plan.set_option("t_fuse", t_fuse)
     sr.plan.upload(pkg.slab.slab_view(u, sr.x_offset, sr.nx), pkg.slab.slab_view(m, sr.x_offset, sr.nx))
     sr.plan.set_sources(src, crd)
     dist.barrier()
     sr.run(0, T // 2)
     sr.run(T // 2 + 1, T - 1)
+    assert sr.plan.get_option("t_fuse_used") == t_fuse
     mine = sr.plan.download()
     gathered = [None] * world
     dist.all_gather_object(gathered, mine)
@@ -142,17 +148,23 @@ def _ipc_worker(rank, world, port, shape, T, S, out_path):
     dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("t_fuse", [1, 2])
 @pytest.mark.parametrize("world", [2, 4, 8])
-def test_one_process_per_gpu_over_ipc(pkg, oracle, tmp_path, world):
+def test_one_process_per_gpu_over_ipc(pkg, oracle, tmp_path, world, t_fuse):
+    """t_fuse = 2: two-step passes, 4-plane ghost zones, the depth negotiated over torch.distributed."""
     import torch
     import torch.multiprocessing as mp
 
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
-    shape, T, S = (32 * world, 64, 128), 12, 6
-    u, m, src, crd = _case(5, shape, T, S, seam_parts=world)
+    shape, T, S = (32 * world, 64, 128), 13, 6
+    if t_fuse == 2:
+        from test_tb2_gpu import fused_case
+        u, m, src, crd = fused_case(5, shape, T, S, seam_parts=world)
+    else:
+        u, m, src, crd = _case(5, shape, T, S, seam_parts=world)
     ref = u.copy()
     oracle.run(ref, m, src, crd, impl="port", threads=8)
     out_path = str(tmp_path / "out.npy")
-    mp.spawn(_ipc_worker, args=(world, _free_port(), shape, T, S, out_path), nprocs=world, join=True)
+    mp.spawn(_ipc_worker, args=(world, _free_port(), shape, T, S, out_path, t_fuse), nprocs=world, join=True)
     assert bits_equal(np.load(out_path), ref)

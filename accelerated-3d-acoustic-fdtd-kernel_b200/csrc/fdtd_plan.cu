@@ -90,6 +90,7 @@ static void plan_free_sources(fdtd_b200_plan *p)
     p->d_plane_off = nullptr;
     p->d_mbase = nullptr;
     p->d_base_idx = nullptr;
+    p->h_base_idx.clear();
     p->ncells_int = p->ncells_halo = p->ncells_all = 0;
     p->n_mbase = 0;
     p->src_size0 = 0;
@@ -173,6 +174,7 @@ int fdtd::plan_create_internal(const PlanShape &s, fdtd_b200_plan **out, bool ca
     p->cfg.stages = env_int("FDTD_B200_STAGES", 0);
     p->cfg.xchunk = env_int("FDTD_B200_XCHUNK", 0);
     p->opt_t_fuse = env_int("FDTD_B200_T_FUSE", g_t_fuse);
+    p->opt_stage_planes = env_int("FDTD_B200_STAGE_PLANES", -1);
 
     cudaError_t e = cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking);
     p->flags_offset = (FDTD_LEVELS * (size_t)p->g.lvl * sizeof(float) + 255) / 256 * 256;
@@ -490,6 +492,7 @@ extern "C" int fdtd_b200_plan_set_sources(fdtd_b200_plan *p, const float *src, i
     FDTD_CHECK(cudaMalloc(&p->d_base_idx, (size_t)p->n_mbase * sizeof(long long)));
     FDTD_CHECK(cudaMemcpy(p->d_base_idx, base_idx.data(), (size_t)p->n_mbase * sizeof(long long), cudaMemcpyHostToDevice));
     p->src_halo_global = tab.halo_global;
+    p->h_base_idx = base_idx;
     p->ncells2 = (int)tab.cells2.size();
     if (!tab.cells2.empty()) {
         FDTD_CHECK(cudaMalloc(&p->d_cells2, tab.cells2.size() * sizeof(SourceCell)));
@@ -525,6 +528,7 @@ static int *option_slot(fdtd_b200_plan *p, const char *key)
     if (!strcmp(key, "stages")) return &p->cfg.stages;
     if (!strcmp(key, "xchunk")) return &p->cfg.xchunk;
     if (!strcmp(key, "t_fuse_agreed")) return &p->t_fuse_agreed;
+    if (!strcmp(key, "stage_planes")) return &p->opt_stage_planes;
     return nullptr;
 }
 
@@ -859,6 +863,207 @@ static int run_many(fdtd_b200_plan **ps, int n, int time_m, int time_M, struct p
         timers->section1 = worst_s1;
     }
     return rc;
+}
+
+// ---------------------------------------------------------------------------- staged run (host arrays in and out)
+// upload -> T time steps -> download as ONE pipeline instead of three phases (what Kernel_* does for its caller:
+// cuda.cu:204-214,232-270,317-320 run them back to back, and at 512^3 the two PCIe transfers are 4x the compute).
+//   * the arrays travel in chunks of B x planes (a plane is contiguous) on a copy stream;
+//   * the time loop is skewed along x: block b advances ALL T steps on planes [bB - 2s, (b+1)B - 2s) for step s
+//     (the stencil has radius 2, so step s of block b only needs step s-1 of blocks b and b-1): block b can run
+//     as soon as chunk b+1 has landed, while later chunks are still on the wire;
+//   * planes that have finished their last step go back to the host on a third stream (PCIe is full duplex),
+//     x-halo planes never change and stay on the host.
+// Every point sees exactly the inputs of the unskewed loop, so results are bit-identical to upload+run+download.
+// section0 = device seconds of the launches of steps >= time_m+5, summed over blocks (events on the compute
+// stream, waits for transfers excluded); section1 = 0 (sources are fused; halo-cell sources take the plain path).
+// Returns cudaErrorNotSupported when the plain path must be taken (nothing has been touched then).
+extern "C" int fdtd_b200_plan_run_staged(fdtd_b200_plan *p, float *h_u, const float *h_m, int time_m, int time_M,
+                                         struct profiler *timers)
+{
+    if (!p || !h_u || !h_m) return (int)cudaErrorInvalidValue;
+    const bool linked = p->link.peer_u[0] || p->link.peer_u[1];
+    const int T = time_M - time_m + 1;
+    const bool src_active = p->ncells_all > 0 && p->src_size0 > 0;
+    const int nx = p->g.X1 - p->g.X0;
+    int B = p->opt_stage_planes;
+    if (B < 0) {
+        // auto: only where the PCIe transfers dominate (a skewed loop is ~(nx + 2T)/B * T small launches), and
+        // blocks long enough to keep that launch count around 1600 (the enqueue must stay ahead of the wire)
+        const long long npts = (long long)nx * (p->g.Y1 - p->g.Y0) * (p->g.Z1 - p->g.Z0);
+        if (npts < 8000000 || T < 1) return (int)cudaErrorNotSupported;
+        B = (int)(((long long)(nx + 2 * T) * T / 1600 + 7) / 8 * 8);
+        B = std::max(16, std::min(B, nx / 2));
+    }
+    if (B < 8 || linked || T < 1 || nx < 2 * B || (src_active && (p->ncells_halo > 0 || !p->opt_fuse))) return (int)cudaErrorNotSupported;
+    FDTD_CHECK(cudaSetDevice(p->dev));
+    if (timers) timers->section0 = timers->section1 = 0.0;
+    const int saved_fuse = p->opt_t_fuse;
+    p->opt_t_fuse = 1;  // one step per launch: the skew is per step (and the transfers hide the compute anyway)
+    int rc = 0;
+    {
+        // kernel choice and tensor maps as in a plain run, but no device-side gather of mbase (m is not there yet)
+        const int n2 = p->ncells2, nall = p->ncells_all;
+        p->ncells2 = p->ncells_all = 0;
+        rc = plan_prepare(p);
+        p->ncells2 = n2;
+        p->ncells_all = nall;
+    }
+    p->opt_t_fuse = saved_fuse;
+    if (rc) return rc;
+    reset_placement(p, 0);
+
+    const Grid g = p->g;
+    const size_t plane = (size_t)g.nyp * g.nzp, lvl = (size_t)g.lvl;
+    cudaStream_t s_up = nullptr, s_down = nullptr;
+    std::vector<cudaEvent_t> ev_up, ev_done, ev_t;
+    auto cleanup = [&](int code) {
+        cudaStreamSynchronize(p->stream);
+        if (s_up) cudaStreamSynchronize(s_up), cudaStreamDestroy(s_up);
+        if (s_down) cudaStreamSynchronize(s_down), cudaStreamDestroy(s_down);
+        for (const std::vector<cudaEvent_t> *v : {&ev_up, &ev_done, &ev_t})
+            for (cudaEvent_t e : *v)
+                if (e) cudaEventDestroy(e);
+        return code;
+    };
+#define STAGED_CHECK(expr)                                   \
+    do {                                                     \
+        cudaError_t _e = (expr);                             \
+        if (_e != cudaSuccess) return cleanup((int)_e);      \
+    } while (0)
+    STAGED_CHECK(cudaStreamCreateWithFlags(&s_up, cudaStreamNonBlocking));
+    STAGED_CHECK(cudaStreamCreateWithFlags(&s_down, cudaStreamNonBlocking));
+    cudaEvent_t tl[4] = {nullptr, nullptr, nullptr, nullptr};  // FDTD_B200_TRACE=1: start, H2D end, compute end, D2H end
+    const bool trace = env_int("FDTD_B200_TRACE", 0) != 0;
+    if (trace) {
+        for (auto &e : tl) STAGED_CHECK(cudaEventCreate(&e));
+        STAGED_CHECK(cudaEventRecord(tl[0], s_up));
+    }
+
+    if (src_active) {  // m at every source's base corner, straight from the host's m
+        std::vector<float> mb((size_t)p->n_mbase, 1.0f);
+        for (int i = 0; i < p->n_mbase; ++i)
+            if (p->h_base_idx[i] >= 0) mb[i] = h_m[p->h_base_idx[i]];
+        STAGED_CHECK(cudaMemcpyAsync(p->d_mbase, mb.data(), mb.size() * sizeof(float), cudaMemcpyHostToDevice, p->stream));
+        STAGED_CHECK(cudaStreamSynchronize(p->stream));
+    }
+
+    // upload chunks: padded planes [c*B, (c+1)*B) of u (three levels) and m
+    const int nchunks = (g.nxp + B - 1) / B;
+    ev_up.resize(nchunks);
+    int uploaded = 0;
+    auto upload_through = [&](int c_last) -> int {
+        for (; uploaded <= c_last && uploaded < nchunks; ++uploaded) {
+            const size_t x0 = (size_t)uploaded * B, n = std::min<size_t>(B, g.nxp - x0) * plane;
+            for (int r = 0; r < 3; ++r)
+                FDTD_CHECK(cudaMemcpyAsync(p->d_u + r * lvl + x0 * plane, h_u + r * lvl + x0 * plane, n * sizeof(float),
+                                           cudaMemcpyHostToDevice, s_up));
+            FDTD_CHECK(cudaMemcpyAsync(p->d_m + x0 * plane, h_m + x0 * plane, n * sizeof(float), cudaMemcpyHostToDevice, s_up));
+            FDTD_CHECK(cudaEventCreateWithFlags(&ev_up[uploaded], cudaEventDisableTiming));
+            FDTD_CHECK(cudaEventRecord(ev_up[uploaded], s_up));
+        }
+        return 0;
+    };
+
+    // one-step launch plan for a block: the streaming kernel with one x chunk per tile
+    TmaPlan tma_block = p->tma;
+    tma_block.xchunk = B;
+    const int first_timed = time_m + FDTD_WARMUP_STEPS;
+    // skewed blocks: b = 0 .. nblocks-1 until the last step's window has passed X1
+    const int nblocks = (nx + 2 * (T - 1) + B - 1) / B;
+    ev_done.resize(nblocks);
+    int downloaded = g.X0;  // padded planes below this are final on the host
+    for (int b = 0; b < nblocks && !rc; ++b) {
+        // step 0 of this block reads up to padded plane X0 + (b+1)B + 1
+        const int need = std::min(g.nxp - 1, g.X0 + (b + 1) * B + 1);
+        if ((rc = upload_through(need / B))) break;
+        STAGED_CHECK(cudaStreamWaitEvent(p->stream, ev_up[std::min(need / B, nchunks - 1)], 0));
+        bool timing = false;
+        for (int s = 0; s < T && !rc; ++s) {
+            const int time = time_m + s;
+            const int lo = std::max(g.X0, g.X0 + b * B - 2 * s), hi = std::min(g.X1, g.X0 + (b + 1) * B - 2 * s);
+            if (hi <= lo) continue;
+            if (time >= first_timed && !timing) {
+                cudaEvent_t e;
+                STAGED_CHECK(cudaEventCreate(&e));
+                STAGED_CHECK(cudaEventRecord(e, p->stream));
+                ev_t.push_back(e);
+                timing = true;
+            }
+            const int t0 = ((time % 3) + 3) % 3, t1 = (((time + 2) % 3) + 3) % 3, t2 = (((time + 1) % 3) + 3) % 3;
+            StepArgs a{};
+            a.u = p->d_u;
+            a.m = p->d_m;
+            a.g = g;
+            a.g.X0 = lo;
+            a.g.X1 = hi;
+            a.k = p->k;
+            a.t0 = t0;
+            a.t1 = t1;
+            a.t2 = t2;
+            if (src_active && time >= 0 && time < p->src_size0 && p->ncells_int > 0) {
+                a.sv.plane_off = p->d_plane_off;
+                a.sv.cells = p->d_cells;
+                a.sv.contribs = p->d_contribs;
+                a.sv.src_row = p->d_src + (size_t)time * p->pstride;
+                a.sv.mbase = p->d_mbase;
+                a.sv.ncells = p->ncells_int;
+            }
+            a.link.depth = 2;
+            rc = p->kernel_used == 2 ? launch_stencil_tma(tma_block, a, p->opt_exact != 0, p->stream)
+                                     : launch_stencil_generic(a, p->opt_exact != 0, p->stream);
+            p->last_launches++;
+        }
+        if (rc) break;
+        if (timing) {
+            cudaEvent_t e;
+            STAGED_CHECK(cudaEventCreate(&e));
+            STAGED_CHECK(cudaEventRecord(e, p->stream));
+            ev_t.push_back(e);
+        }
+        STAGED_CHECK(cudaEventCreateWithFlags(&ev_done[b], cudaEventDisableTiming));
+        STAGED_CHECK(cudaEventRecord(ev_done[b], p->stream));
+        // planes below X0 + (b+1)B - 2(T-1) have been through all T steps
+        const int fin = b == nblocks - 1 ? g.X1 : std::min(g.X1, g.X0 + (b + 1) * B - 2 * (T - 1));
+        if (fin > downloaded) {
+            STAGED_CHECK(cudaStreamWaitEvent(s_down, ev_done[b], 0));
+            const size_t n = (size_t)(fin - downloaded) * plane;
+            for (int r = 0; r < 3; ++r)
+                STAGED_CHECK(cudaMemcpyAsync(h_u + r * lvl + (size_t)downloaded * plane, p->d_u + r * lvl + (size_t)downloaded * plane,
+                                             n * sizeof(float), cudaMemcpyDeviceToHost, s_down));
+            downloaded = fin;
+        }
+    }
+    if (!rc) rc = upload_through(nchunks - 1);  // trailing halo planes (the device copy stays complete for later runs)
+    if (rc) return cleanup(rc);
+    if (trace) {
+        cudaEventRecord(tl[1], s_up);
+        cudaEventRecord(tl[2], p->stream);
+        cudaEventRecord(tl[3], s_down);
+    }
+    STAGED_CHECK(cudaStreamSynchronize(s_up));
+    STAGED_CHECK(cudaStreamSynchronize(p->stream));
+    STAGED_CHECK(cudaStreamSynchronize(s_down));
+    if (trace) {
+        float t1 = 0.f, t2 = 0.f, t3 = 0.f;
+        cudaEventElapsedTime(&t1, tl[0], tl[1]);
+        cudaEventElapsedTime(&t2, tl[0], tl[2]);
+        cudaEventElapsedTime(&t3, tl[0], tl[3]);
+        fprintf(stderr, "[fdtd_b200] staged: %d blocks of %d planes, %ld launches; H2D done at %.2f ms, compute at %.2f, D2H at %.2f\n",
+                nblocks, B, p->last_launches, t1, t2, t3);
+        for (auto &e : tl) cudaEventDestroy(e);
+    }
+    double s0 = 0.0;
+    for (size_t i = 0; i + 1 < ev_t.size(); i += 2) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ev_t[i], ev_t[i + 1]);
+        s0 += ms * 1e-3;
+    }
+    const int ntimed = time_M >= first_timed ? time_M - first_timed + 1 : 0;
+    p->last_kernel_seconds = ntimed > 0 ? s0 / ntimed : 0.0;
+    if (timers) timers->section0 = s0;
+#undef STAGED_CHECK
+    return cleanup(0);
 }
 
 extern "C" int fdtd_b200_plan_run(fdtd_b200_plan *p, int time_m, int time_M, struct profiler *timers)

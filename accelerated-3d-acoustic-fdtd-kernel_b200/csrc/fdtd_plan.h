@@ -3,6 +3,8 @@
 #include "../../include/fdtd_b200.h"
 #include "fdtd_kernels.cuh"
 
+#include <vector>
+
 namespace fdtd {
 
 // Array shape and update extents exactly as the reference ABI passes them (unpadded, inclusive).
@@ -49,9 +51,11 @@ struct fdtd_b200_plan {
     int *d_plane_off2 = nullptr;
     int ncells2 = 0;
     bool src_halo_global = false;
+    std::vector<long long> h_base_idx;  // host copy of d_base_idx (the staged run gathers mbase from the host's m)
 
     // options
     int opt_kernel = 0, opt_exact = 1, opt_fuse = 1, opt_graph = 0, opt_t_fuse = 1;
+    int opt_stage_planes = -1;       // x planes per block of the staged (pipelined H2D / compute / D2H) run; -1 = auto, 0 = off
     fdtd::TmaConfig cfg{};
     fdtd::TmaPlan tma{};
     fdtd::Tb2Plan tb2{};

@@ -104,6 +104,7 @@ def lib():
     L.fdtd_b200_plan_fill_dense.restype, L.fdtd_b200_plan_fill_dense.argtypes = i, [vp]
     L.fdtd_b200_plan_set_sources.restype, L.fdtd_b200_plan_set_sources.argtypes = i, [vp, vp, i, i, vp, i, i, i, i]
     L.fdtd_b200_plan_run.restype, L.fdtd_b200_plan_run.argtypes = i, [vp, i, i, C.POINTER(Profiler)]
+    L.fdtd_b200_plan_run_staged.restype, L.fdtd_b200_plan_run_staged.argtypes = i, [vp, vp, vp, i, i, C.POINTER(Profiler)]
     L.fdtd_b200_plan_last_launches.restype, L.fdtd_b200_plan_last_launches.argtypes = C.c_long, [vp]
     L.fdtd_b200_plan_last_kernel_seconds.restype, L.fdtd_b200_plan_last_kernel_seconds.argtypes = d, [vp]
     L.fdtd_b200_plan_set_option.restype, L.fdtd_b200_plan_set_option.argtypes = i, [vp, C.c_char_p, i]
@@ -133,7 +134,7 @@ def exported_symbols():
         "Kernel_CUDA_Optimized", "Kernel_B200", "FDTD_SetRuntimeConfig",
         "fdtd_b200_plan_create", "fdtd_b200_plan_destroy", "fdtd_b200_plan_u", "fdtd_b200_plan_m",
         "fdtd_b200_plan_level", "fdtd_b200_plan_probe_fuse", "fdtd_b200_plan_level_elems", "fdtd_b200_plan_upload", "fdtd_b200_plan_download", "fdtd_b200_plan_fill",
-        "fdtd_b200_plan_fill_dense", "fdtd_b200_plan_set_sources", "fdtd_b200_plan_run",
+        "fdtd_b200_plan_fill_dense", "fdtd_b200_plan_set_sources", "fdtd_b200_plan_run", "fdtd_b200_plan_run_staged",
         "fdtd_b200_plan_last_launches", "fdtd_b200_plan_last_kernel_seconds", "fdtd_b200_plan_set_option",
         "fdtd_b200_plan_get_option", "fdtd_b200_plan_ipc_export", "fdtd_b200_plan_ipc_attach",
         "fdtd_b200_plan_attach_local", "fdtd_b200_run_slabs", "fdtd_b200_source_table", "fdtd_b200_slab_source_cells", "fdtd_b200_fill_ricker",
@@ -328,6 +329,19 @@ class Plan:
     def run(self, time_m: int, time_M: int) -> Profiler:
         t = Profiler(0.0, 0.0)
         _check(lib().fdtd_b200_plan_run(self._h, time_m, time_M, C.byref(t)), "fdtd_b200_plan_run")
+        return t
+
+    def run_staged(self, u: np.ndarray, m: np.ndarray, time_m: int, time_M: int):
+        """upload + run + download as one pipeline (u is updated in place).  Returns the Profiler, or None when
+        the library asks for the three-phase path (cudaErrorNotSupported)."""
+        for a, shp in ((u, self.shape), (m, self.shape[1:])):
+            if not (a.dtype == np.float32 and a.flags.c_contiguous and a.shape == shp):
+                raise TypeError("run_staged expects C-contiguous float32 arrays of the padded shape")
+        t = Profiler(0.0, 0.0)
+        rc = lib().fdtd_b200_plan_run_staged(self._h, u.ctypes.data, m.ctypes.data, time_m, time_M, C.byref(t))
+        if rc == 801:
+            return None
+        _check(rc, "fdtd_b200_plan_run_staged")
         return t
 
     def set_option(self, key: str, value: int):

@@ -129,6 +129,18 @@ int fdtd_b200_plan_set_sources(fdtd_b200_plan *plan, const float *src, int src_s
  */
 int fdtd_b200_plan_run(fdtd_b200_plan *plan, int time_m, int time_M, struct profiler *timers);
 
+/*
+ * upload + run + download as one pipeline, for host arrays h_u [3][nxp][nyp][nzp] (in/out) and h_m (what
+ * Kernel_* does with its caller's buffers): the arrays travel in chunks of x planes, the time loop is skewed
+ * along x so a block of planes runs all its steps as soon as its chunk has landed, and finished planes go
+ * back while later chunks are still arriving (PCIe is full duplex).  Bit-identical to upload, run, download.
+ * Option "stage_planes" = planes per block (-1 = auto: grids of >= 8M points, blocks sized for ~1600 launches;
+ * 0 = off).  Returns cudaErrorNotSupported (801) when the three-phase path must be used instead: linked slabs,
+ * sources that touch halo cells, fewer than 2 blocks, or (auto) a grid too small to gain.
+ */
+int fdtd_b200_plan_run_staged(fdtd_b200_plan *plan, float *h_u, const float *h_m, int time_m, int time_M,
+                              struct profiler *timers);
+
 /* Number of kernel launches issued by the last run (stencil + scatter + halo kernels). */
 long fdtd_b200_plan_last_launches(fdtd_b200_plan *plan);
 /* Average stencil-kernel seconds per launch in the timed region of the last run. */

@@ -21,18 +21,22 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// Blocks until the phase with this parity has completed.  The suspend-time hint lets the hardware park the warp
+// until the barrier flips (or the hint expires) instead of returning after a short system-defined time: without
+// it a quarter of all issued instructions of the two-step kernel were try_wait retries of warps that were ahead
+// (profiles/r01_ncu_tb2_32x64_exact0.txt), competing for issue slots with the warps they were waiting for.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
         "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
         "@p bra WAIT_DONE;\n"
         "bra WAIT_LOOP;\n"
         "WAIT_DONE:\n"
         "}\n" ::"r"(bar),
-        "r"(parity)
+        "r"(parity), "r"(0x989680)
         : "memory");
 }
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1,

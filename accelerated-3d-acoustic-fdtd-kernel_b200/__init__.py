@@ -25,6 +25,7 @@ from .host import (  # noqa: F401
     lib_path,
     run_slabs,
     slab_source_cells,
+    slab_source_cells2,
     source_table,
     write_benchmark_csv,
 )

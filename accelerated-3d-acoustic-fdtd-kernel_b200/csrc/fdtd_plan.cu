@@ -461,6 +461,37 @@ extern "C" int fdtd_b200_slab_source_cells(const fdtd_b200_geometry *geo, const 
     return 0;
 }
 
+// Host-only view of the table two-step launches use: the slab's interior cells plus the cells on the neighbour
+// slabs' two nearest planes (a pass recomputes those planes), sorted by (X,Y,Z).  halo_global: some in-range
+// corner of some source is a halo cell of the GLOBAL grid (then no slab runs two-step launches).
+extern "C" int fdtd_b200_slab_source_cells2(const fdtd_b200_geometry *geo, const float *coords, int ncoords, int cstride,
+                                            int p_src_m, int p_src_M, int max_cells, int *cells, int *ncells,
+                                            int max_contribs, int *contrib_p, float *contrib_w, int *ncontribs,
+                                            int *halo_global)
+{
+    if (!geo || !coords || p_src_m < 0 || p_src_M >= ncoords || cstride < 3) return (int)cudaErrorInvalidValue;
+    PlanShape s;
+    Grid g;
+    shape_from_geometry(geo, s);
+    grid_from_shape(s, g);
+    SourceTable t;
+    build_source_table(s, g, coords, cstride, p_src_m, p_src_M, t);
+    if ((int)t.cells2.size() > max_cells || (int)t.contribs.size() > max_contribs) return (int)cudaErrorInvalidValue;
+    for (size_t i = 0; i < t.cells2.size(); ++i) {
+        const SourceCell &c = t.cells2[i];
+        int *o = cells + 5 * i;
+        o[0] = c.X; o[1] = c.Y; o[2] = c.Z; o[3] = c.first; o[4] = c.count;
+    }
+    for (size_t i = 0; i < t.contribs.size(); ++i) {
+        contrib_p[i] = t.contribs[i].p;
+        contrib_w[i] = t.contribs[i].w;
+    }
+    if (ncells) *ncells = (int)t.cells2.size();
+    if (ncontribs) *ncontribs = (int)t.contribs.size();
+    if (halo_global) *halo_global = t.halo_global ? 1 : 0;
+    return 0;
+}
+
 extern "C" int fdtd_b200_plan_set_sources(fdtd_b200_plan *p, const float *src, int src_size0, int pstride,
                                           const float *coords, int ncoords, int cstride, int p_src_m, int p_src_M)
 {

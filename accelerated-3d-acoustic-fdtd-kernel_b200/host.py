@@ -119,6 +119,9 @@ def lib():
     L.fdtd_b200_slab_source_cells.restype = i
     L.fdtd_b200_slab_source_cells.argtypes = [C.POINTER(Geometry), vp, i, i, i, i, i, vp, C.POINTER(i), C.POINTER(i), i, vp, vp,
                                               C.POINTER(i), vp]
+    L.fdtd_b200_slab_source_cells2.restype = i
+    L.fdtd_b200_slab_source_cells2.argtypes = [C.POINTER(Geometry), vp, i, i, i, i, i, vp, C.POINTER(i), i, vp, vp, C.POINTER(i),
+                                               C.POINTER(i)]
     L.fdtd_b200_fill_ricker.restype, L.fdtd_b200_fill_ricker.argtypes = None, [vp, i, i, f]
     L.fdtd_b200_fill_source_coords.restype, L.fdtd_b200_fill_source_coords.argtypes = None, [vp, i, i, i, i, f, f, f]
     L.fdtd_b200_write_benchmark_csv.restype = i
@@ -137,7 +140,7 @@ def exported_symbols():
         "fdtd_b200_plan_fill_dense", "fdtd_b200_plan_set_sources", "fdtd_b200_plan_run", "fdtd_b200_plan_run_staged",
         "fdtd_b200_plan_last_launches", "fdtd_b200_plan_last_kernel_seconds", "fdtd_b200_plan_set_option",
         "fdtd_b200_plan_get_option", "fdtd_b200_plan_ipc_export", "fdtd_b200_plan_ipc_attach",
-        "fdtd_b200_plan_attach_local", "fdtd_b200_run_slabs", "fdtd_b200_source_table", "fdtd_b200_slab_source_cells", "fdtd_b200_fill_ricker",
+        "fdtd_b200_plan_attach_local", "fdtd_b200_run_slabs", "fdtd_b200_source_table", "fdtd_b200_slab_source_cells", "fdtd_b200_slab_source_cells2", "fdtd_b200_fill_ricker",
         "fdtd_b200_fill_source_coords", "fdtd_b200_write_benchmark_csv", "fdtd_b200_version",
     ]
 
@@ -235,6 +238,22 @@ def slab_source_cells(geom: Geometry, coords, p_src_m=0, p_src_M=None):
                                              cp.shape[0], cp.ctypes.data, cw.ctypes.data, C.byref(n_c), base.ctypes.data),
            "fdtd_b200_slab_source_cells")
     return cells[:n_all.value], n_int.value, cp[:n_c.value], cw[:n_c.value], base[:p_src_M + 1]
+
+
+def slab_source_cells2(geom: Geometry, coords, p_src_m=0, p_src_M=None):
+    """Host-only table of the two-step launches -> (cells[n,5], contrib_p, contrib_w, halo_global)."""
+    coords = np.ascontiguousarray(coords, np.float32)
+    p_src_M = coords.shape[0] - 1 if p_src_M is None else p_src_M
+    nsrc = max(0, p_src_M - p_src_m + 1)
+    cells = np.zeros((16 * nsrc + 1, 5), np.int32)
+    cp = np.zeros(16 * nsrc + 1, np.int32)
+    cw = np.zeros(16 * nsrc + 1, np.float32)
+    n_all, n_c, hg = C.c_int(), C.c_int(), C.c_int()
+    _check(lib().fdtd_b200_slab_source_cells2(C.byref(geom), coords.ctypes.data, coords.shape[0], coords.shape[1], p_src_m,
+                                              p_src_M, cells.shape[0], cells.ctypes.data, C.byref(n_all), cp.shape[0],
+                                              cp.ctypes.data, cw.ctypes.data, C.byref(n_c), C.byref(hg)),
+           "fdtd_b200_slab_source_cells2")
+    return cells[:n_all.value], cp[:n_c.value], cw[:n_c.value], bool(hg.value)
 
 
 def write_benchmark_csv(filename, method, total, s0, s1, device, overhead, gflops, gbps, peak_fp32_gf, peak_bw_gbs,

@@ -196,6 +196,12 @@ int fdtd_b200_slab_source_cells(const fdtd_b200_geometry *geom, const float *coo
                                 int p_src_m, int p_src_M, int max_cells, int *cells, int *ncells_int,
                                 int *ncells_all, int max_contribs, int *contrib_p, float *contrib_w,
                                 int *ncontribs, long long *base_idx);
+/* The table two-step launches use (host only): interior cells plus the cells on the neighbour slabs' two nearest
+ * planes, sorted by (X,Y,Z); *halo_global = 1 when some source corner of the GLOBAL grid is a halo cell. */
+int fdtd_b200_slab_source_cells2(const fdtd_b200_geometry *geom, const float *coords, int ncoords, int cstride,
+                                 int p_src_m, int p_src_M, int max_cells, int *cells, int *ncells,
+                                 int max_contribs, int *contrib_p, float *contrib_w, int *ncontribs,
+                                 int *halo_global);
 /* The driver's input generators (main.cpp:290-298 and 301-325), fp32. */
 void fdtd_b200_fill_ricker(float *src, int T, int S, float dt);
 void fdtd_b200_fill_source_coords(float *coords, int S, int nx, int ny, int nz, float h_x, float h_y,

@@ -142,3 +142,139 @@ def test_slab_source_ownership_partitions_the_global_table(pkg):
         assert all(4 <= X < 4 + nx and 4 <= Y < 4 + ny and 4 <= Z < 4 + nz for X, Y, Z, _, _ in c2[:ni2])
         assert list(c2[:ni2, 0]) == sorted(c2[:ni2, 0])
     assert len(got) == len(set(got)) == len(want) and set(got) == want
+
+
+# ------------------------------------------------------------------ two-step launches: ghost-zone source cells, 4-plane exchange
+def test_two_step_source_table_covers_the_neighbours_nearest_planes(pkg):
+    """A two-step launch recomputes the neighbour slabs' two nearest planes of u^{n+1}, so its table holds the
+    slab's interior cells plus the global table's cells on those planes -- same (source, weight) lists."""
+    rng = np.random.default_rng(8)
+    nxg, ny, nz = 30, 10, 12
+    crd = (rng.uniform(0.03, 0.96, (60, 3)) * (np.array([nxg, ny, nz], np.float32) - 1) * np.float32(0.1)).astype(np.float32)
+    for k, x in enumerate((9, 10, 8, 11, 19, 20, 18, 21)):  # on and next to the seams of [0,10) [10,20) [20,30)
+        crd[k, 0] = np.float32(x * 0.1) + np.float32(0.03)
+    whole = pkg.Geometry(nxg, ny, nz, 0, nxg, 1e-3, 0.1, 0.1, 0.1, 0, 0, 0, -1)
+    cells, cp, cw, halo = pkg.slab_source_cells2(whole, crd)
+    c1, n_int, cp1, cw1, _ = pkg.slab_source_cells(whole, crd)
+    assert not halo and len(cells) == n_int == len(c1)  # one slab: exactly the interior cells
+    glob = {}
+    for X, Y, Z, f, c in cells:
+        glob[(int(X), int(Y), int(Z))] = [(int(cp[k]), float(cw[k])) for k in range(f, f + c)]
+    for r, (off, nx) in enumerate(pkg.partition(nxg, 3)):
+        g = pkg.Geometry(nx, ny, nz, off, nxg, 1e-3, 0.1, 0.1, 0.1, 0, 0, 0, -1)
+        c2, cp2, cw2, halo2 = pkg.slab_source_cells2(g, crd)
+        assert not halo2
+        lo = 4 - (2 if r > 0 else 0)
+        hi = 4 + nx + (2 if r < 2 else 0)
+        want = {k: v for k, v in glob.items() if lo <= k[0] - off < hi}
+        got = {(int(X) + off, int(Y), int(Z)): [(int(cp2[k]), float(cw2[k])) for k in range(f, f + c)] for X, Y, Z, f, c in c2}
+        assert got == want
+        assert [tuple(c[:3]) for c in c2] == sorted(tuple(c[:3]) for c in c2)  # plane order: the kernel indexes by plane
+    # a corner in a halo cell anywhere is seen by EVERY slab (they must all fall back to one step per launch)
+    crd[5, 1] = np.float32(-0.04)
+    for off, nx in pkg.partition(nxg, 3):
+        g = pkg.Geometry(nx, ny, nz, off, nxg, 1e-3, 0.1, 0.1, 0.1, 0, 0, 0, -1)
+        assert pkg.slab_source_cells2(g, crd)[3]
+
+
+def _worker_two_step(rank, world, port, shape, T, S, out_path):
+    """Each rank advances its slab in two-step passes with the ORACLE as the compute step (test only): step n on the
+    slab's planes plus the neighbours' two nearest planes (sources from the product's two-step table), step n+1 on
+    its own planes, then 2 planes of u^{n+1} and 4 planes of u^{n+2} go to each neighbour."""
+    import importlib
+    import sys
+
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    pkg = importlib.import_module(PKG_NAME)
+    from oracle import oracle as O
+
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    nxg, ny, nz = shape
+    rng = np.random.default_rng(123)
+    u_g = rng.uniform(-1, 1, (3, nxg + 8, ny + 8, nz + 8)).astype(np.float32)
+    m_g = rng.uniform(0.5, 3.0, (nxg + 8, ny + 8, nz + 8)).astype(np.float32)
+    src = rng.uniform(-20, 20, (T, S)).astype(np.float32)
+    crd = (rng.uniform(0.05, 0.95, (S, 3)) * (np.array(shape, np.float32) - 1) * np.float32(0.1)).astype(np.float32)
+    parts = pkg.partition(nxg, world)
+    for i, (off, _) in enumerate(parts[1:]):  # sources on, and one / two planes off, every seam
+        for j, dx in enumerate((-1, 0, -2, 1)):
+            crd[(4 * i + j) % S, 0] = np.float32((off + dx) * 0.1) + np.float32(0.03)
+    off, nx = parts[rank]
+    u = pkg.slab.slab_view(u_g, off, nx)
+    m = pkg.slab.slab_view(m_g, off, nx)
+    geom = pkg.Geometry(nx, ny, nz, off, nxg, 1e-3, 0.1, 0.1, 0.1, 0.0, 0.0, 0.0, -1)
+    cells2, cp, cw, halo = pkg.slab_source_cells2(geom, crd)
+    assert not halo
+    # base corner of every source in LOCAL padded coordinates (the ghost planes hold the neighbours' m)
+    base = {}
+    for p in range(S):
+        pos, _, _, _ = pkg.source_table(crd[p], (0, 0, 0), (0.1,) * 3, (0, 0, 0), (nxg - 1, ny - 1, nz - 1))
+        base[p] = (int(pos[0]) - off + 4, int(pos[1]) + 4, int(pos[2]) + 4)
+    X0, X1 = 4, 4 + nx
+    lo2 = 2 if rank > 0 else 0
+    hi2 = 2 if rank < world - 1 else 0
+
+    def inject(level, time, planes):
+        for X, Y, Z, first, count in cells2:
+            if not (planes[0] <= X < planes[1]):
+                continue
+            v = u[level, X, Y, Z]
+            for k in range(first, first + count):
+                p = int(cp[k])
+                v = np.float32(v + np.float32(np.float32(cw[k] * src[time, p]) / m[base[p]]))
+            u[level, X, Y, Z] = v
+
+    def exchange(level, depth):
+        reqs, bufs = [], {}
+        if rank > 0:
+            reqs.append(dist.isend(torch.from_numpy(u[level, X0:X0 + depth].copy()), rank - 1))
+            bufs["lo"] = torch.empty((depth, ny + 8, nz + 8), dtype=torch.float32)
+            reqs.append(dist.irecv(bufs["lo"], rank - 1))
+        if rank < world - 1:
+            reqs.append(dist.isend(torch.from_numpy(u[level, X1 - depth:X1].copy()), rank + 1))
+            bufs["hi"] = torch.empty((depth, ny + 8, nz + 8), dtype=torch.float32)
+            reqs.append(dist.irecv(bufs["hi"], rank + 1))
+        for r in reqs:
+            r.wait()
+        if "lo" in bufs:
+            u[level, X0 - depth:X0] = bufs["lo"].numpy()
+        if "hi" in bufs:
+            u[level, X1:X1 + depth] = bufs["hi"].numpy()
+
+    time = 0
+    while time < T:
+        t2 = (time + 1) % 3
+        if time + 1 < T:  # a two-step pass
+            # step n on [X0-2, X1+2) towards neighbours: extents are unpadded, local x index = padded - 4
+            O.run(u, m, time_m=time, time_M=time, impl="port", extents=(-lo2, nx - 1 + hi2, 0, ny - 1, 0, nz - 1))
+            inject(t2, time, (X0 - lo2, X1 + hi2))
+            O.run(u, m, time_m=time + 1, time_M=time + 1, impl="port")
+            inject((time + 2) % 3, time + 1, (X0, X1))
+            exchange(t2, 2)
+            exchange((time + 2) % 3, 4)
+            time += 2
+        else:  # odd remainder: one step, 4 planes out (a pass may follow in a later run)
+            O.run(u, m, time_m=time, time_M=time, impl="port")
+            inject(t2, time, (X0, X1))
+            exchange(t2, 4)
+            time += 1
+    gathered = [None] * world
+    dist.all_gather_object(gathered, u)
+    if rank == 0:
+        out = np.zeros_like(u_g)
+        pkg.slab.assemble(out, gathered, parts)
+        ref = u_g.copy()
+        O.run(ref, m_g, src, crd, impl="port")
+        np.save(out_path, np.array([bits_equal(out, ref), float(np.abs(out - ref).max())]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,shape,T", [(2, (16, 8, 12), 7), (3, (21, 8, 8), 6)])
+def test_two_step_slab_passes_match_single_domain(pkg, oracle, tmp_path, world, shape, T):
+    out = str(tmp_path / "res2.npy")
+    mp.spawn(_worker_two_step, args=(world, _free_port(), shape, T, 9, out), nprocs=world, join=True)
+    ok, err = np.load(out)
+    assert ok == 1.0, f"two-step slab passes differ from the single-domain oracle (max abs {err})"

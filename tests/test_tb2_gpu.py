@@ -149,13 +149,17 @@ def test_benchmark_config_matches_golden_with_two_step_passes(pkg, oracle, golde
     g = meta["bench256_s1"]
     u, m, src, crd = bench_inputs(oracle, g["n"], g["T"], g["S"])
     n = g["n"]
+    import os
+
     pkg.FDTD_SetRuntimeConfig(1, 2, 1)
+    os.environ["FDTD_B200_STAGE_PLANES"] = "0"  # three-phase path: the staged run uses one-step launches
     try:
         t = pkg.Profiler(0.0, 0.0)
         rc = pkg.Kernel_CUDA_Optimized(m, src, crd, u, n - 1, 0, n - 1, 0, n - 1, 0, 1e-3, 0.1, 0.1, 0.1, 0.0, 0.0, 0.0,
                                        g["S"] - 1, 0, g["T"] - 1, 0, 0, 1, t)
     finally:
         pkg.FDTD_SetRuntimeConfig(1, 1, 1)
+        del os.environ["FDTD_B200_STAGE_PLANES"]
     assert rc == 0
     assert hashlib.sha256(np.ascontiguousarray(u).tobytes()).hexdigest() == g["sha256"]
     assert t.section0 > 0 and t.section1 == 0.0
@@ -239,3 +243,31 @@ def test_512_two_step_equals_one_step(pkg):
             res[tf] = p.download()
     assert float(np.abs(res[1]).max()) == pytest.approx(0.116841748, rel=1e-6)
     assert bits_equal(res[1], res[2])
+
+
+def test_512_bench_headline_configuration_within_tolerance(pkg, oracle):
+    """bench.py's headline configuration (contracted arithmetic, two time steps per launch) against the bit-exact
+    one-step run at the full BASELINE size: relative L2 < 1e-4 (README.md:33) and max-abs <= 1e-5 x peak |u|
+    (BASELINE.json north_star), denormals kept."""
+    n, T = 512, 50
+    src, crd = pkg.fill_ricker(T, 1), pkg.fill_source_coords(1, n, n, n)
+    with pkg.Plan(n, n, n, deviceid=0) as p:
+        p.set_sources(src, crd)
+        p.fill(0.0, 1.5)
+        p.run(0, T - 1)
+        ref = p.download()
+        p.set_option("exact", 0)
+        p.set_option("t_fuse", 2)
+        p.fill(0.0, 1.5)
+        p.run(0, T - 1)
+        assert p.get_option("t_fuse_used") == 2 and p.get_option("exact") == 0
+        out = p.download()
+    # the wavefield lives in the low 168^3 corner (test_512_properties); everything else is exactly zero in both
+    w = slice(0, 176)
+    assert not out[:, 176:].any() and not ref[:, 176:].any()
+    a, b = out[:, w, w, w].astype(np.float64), ref[:, w, w, w].astype(np.float64)
+    rel = np.sqrt(((a - b) ** 2).sum() / (b ** 2).sum())
+    assert rel < REL_L2_TOL, rel
+    assert np.abs(a - b).max() <= 1e-5 * np.abs(b).max()
+    den = (np.abs(ref) < np.finfo(np.float32).tiny) & (ref != 0)
+    assert den.any() and np.count_nonzero(out[den]) > 0.9 * den.sum()

@@ -14,9 +14,14 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <deque>
+#include <functional>
 #include <fstream>
 #include <map>
 #include <mutex>
+#include <thread>
 #include <tuple>
 #include <vector>
 
@@ -896,6 +901,80 @@ static int run_many(fdtd_b200_plan **ps, int n, int time_m, int time_M, struct p
     return rc;
 }
 
+// ---------------------------------------------------------------------------- pinned bounce buffers
+// Callers like the reference driver hand over pageable arrays (new float[], main.cpp:345-346): the driver would stage
+// every cudaMemcpyAsync itself, synchronously, and the staged run below would fall back to one phase after the
+// other.  Instead host threads copy chunk by chunk between the caller's arrays and a small ring of pinned buffers,
+// and the DMA engines work on those.  The buffers are cached per process (page-locking 0.5 GB costs more than a run).
+namespace {
+struct StagingCache {
+    std::mutex mu;
+    void *up[3] = {nullptr, nullptr, nullptr};
+    void *dn[2] = {nullptr, nullptr};
+    size_t up_bytes = 0, dn_bytes = 0;
+    bool busy = false;
+} g_staging;
+
+int staging_acquire(size_t up_bytes, size_t dn_bytes)
+{
+    std::lock_guard<std::mutex> lk(g_staging.mu);
+    if (g_staging.busy) return (int)cudaErrorNotReady;
+    if (g_staging.up_bytes < up_bytes) {
+        for (void *&q : g_staging.up) {
+            cudaFreeHost(q);
+            q = nullptr;
+        }
+        g_staging.up_bytes = 0;
+        for (void *&q : g_staging.up) FDTD_CHECK(cudaHostAlloc(&q, up_bytes, cudaHostAllocDefault));
+        g_staging.up_bytes = up_bytes;
+    }
+    if (g_staging.dn_bytes < dn_bytes) {
+        for (void *&q : g_staging.dn) {
+            cudaFreeHost(q);
+            q = nullptr;
+        }
+        g_staging.dn_bytes = 0;
+        for (void *&q : g_staging.dn) FDTD_CHECK(cudaHostAlloc(&q, dn_bytes, cudaHostAllocDefault));
+        g_staging.dn_bytes = dn_bytes;
+    }
+    g_staging.busy = true;
+    return 0;
+}
+void staging_release()
+{
+    std::lock_guard<std::mutex> lk(g_staging.mu);
+    g_staging.busy = false;
+}
+
+// memcpy split over k threads (one thread moves ~10 GB/s; the two PCIe directions want ~50 each)
+void par_memcpy(void *dst, const void *src, size_t bytes, int k)
+{
+    if (k <= 1 || bytes < (size_t)(4 << 20)) {
+        memcpy(dst, src, bytes);
+        return;
+    }
+    const size_t part = ((bytes + k - 1) / k + 4095) / 4096 * 4096;
+    std::vector<std::thread> th;
+    for (int i = 1; i < k; ++i) {
+        const size_t off = (size_t)i * part;
+        if (off >= bytes) break;
+        th.emplace_back([=] { memcpy((char *)dst + off, (const char *)src + off, std::min(part, bytes - off)); });
+    }
+    memcpy(dst, src, std::min(part, bytes));
+    for (auto &t : th) t.join();
+}
+
+bool is_pinned(const void *q)
+{
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, q) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeHost;
+}
+}  // namespace
+
 // ---------------------------------------------------------------------------- staged run (host arrays in and out)
 // upload -> T time steps -> download as ONE pipeline instead of three phases (what Kernel_* does for its caller:
 // cuda.cu:204-214,232-270,317-320 run them back to back, and at 512^3 the two PCIe transfers are 4x the compute).
@@ -948,7 +1027,9 @@ extern "C" int fdtd_b200_plan_run_staged(fdtd_b200_plan *p, float *h_u, const fl
     const size_t plane = (size_t)g.nyp * g.nzp, lvl = (size_t)g.lvl;
     cudaStream_t s_up = nullptr, s_down = nullptr;
     std::vector<cudaEvent_t> ev_up, ev_done, ev_t;
+    std::function<void()> stop_threads = [] {};
     auto cleanup = [&](int code) {
+        stop_threads();
         cudaStreamSynchronize(p->stream);
         if (s_up) cudaStreamSynchronize(s_up), cudaStreamDestroy(s_up);
         if (s_down) cudaStreamSynchronize(s_down), cudaStreamDestroy(s_down);
@@ -964,6 +1045,41 @@ extern "C" int fdtd_b200_plan_run_staged(fdtd_b200_plan *p, float *h_u, const fl
     } while (0)
     STAGED_CHECK(cudaStreamCreateWithFlags(&s_up, cudaStreamNonBlocking));
     STAGED_CHECK(cudaStreamCreateWithFlags(&s_down, cudaStreamNonBlocking));
+    // pageable caller arrays: go through the pinned bounce ring with host threads (see above)
+    const int nchunks = (g.nxp + B - 1) / B;
+    const bool bounce = env_int("FDTD_B200_BOUNCE", (is_pinned(h_u) && is_pinned(h_m)) ? 0 : 1) != 0;
+    const int kthreads = std::max(1, std::min(env_int("FDTD_B200_COPY_THREADS", 8), (int)std::thread::hardware_concurrency() / 2));
+    bool have_staging = false;
+    if (bounce) {
+        const int rs = staging_acquire(4 * (size_t)B * plane * sizeof(float), 3 * (size_t)B * plane * sizeof(float));
+        if (rs) return cleanup(rs == (int)cudaErrorNotReady ? (int)cudaErrorNotSupported : rs);
+        have_staging = true;
+    }
+    struct DownJob {
+        cudaEvent_t after;
+        int x0, n;
+    };
+    std::mutex mu;
+    std::condition_variable cv;
+    int up_ready = 0;             // chunks whose H2D copies are enqueued (ev_up recorded)
+    std::deque<DownJob> jobs;
+    bool jobs_closed = false;
+    std::atomic<int> thread_rc{0};
+    std::thread t_up, t_down;
+    auto join_threads = [&] {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            jobs_closed = true;
+        }
+        cv.notify_all();
+        if (t_up.joinable()) t_up.join();
+        if (t_down.joinable()) t_down.join();
+        if (have_staging) staging_release(), have_staging = false;
+    };
+    stop_threads = [&] {
+        if (t_up.joinable() || t_down.joinable()) thread_rc.store(thread_rc.load() ? thread_rc.load() : (int)cudaErrorUnknown);
+        join_threads();
+    };
     cudaEvent_t tl[4] = {nullptr, nullptr, nullptr, nullptr};  // FDTD_B200_TRACE=1: start, H2D end, compute end, D2H end
     const bool trace = env_int("FDTD_B200_TRACE", 0) != 0;
     if (trace) {
@@ -980,10 +1096,86 @@ extern "C" int fdtd_b200_plan_run_staged(fdtd_b200_plan *p, float *h_u, const fl
     }
 
     // upload chunks: padded planes [c*B, (c+1)*B) of u (three levels) and m
-    const int nchunks = (g.nxp + B - 1) / B;
     ev_up.resize(nchunks);
+    if (bounce) {
+        for (auto &e : ev_up) STAGED_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        t_up = std::thread([&] {  // pack a chunk into a pinned slot with host threads, then hand it to the DMA engine
+            cudaSetDevice(p->dev);
+            for (int c = 0; c < nchunks && !thread_rc.load(); ++c) {
+                const size_t x0 = (size_t)c * B, n = std::min<size_t>(B, g.nxp - x0) * plane;
+                float *slot = static_cast<float *>(g_staging.up[c % 3]);
+                cudaError_t e = c >= 3 ? cudaEventSynchronize(ev_up[c - 3]) : cudaSuccess;  // the slot's previous chunk has left
+                for (int r = 0; r < 4 && e == cudaSuccess; ++r) {
+                    const float *srcp = r < 3 ? h_u + r * lvl + x0 * plane : h_m + x0 * plane;
+                    float *dstp = r < 3 ? p->d_u + r * lvl + x0 * plane : p->d_m + x0 * plane;
+                    par_memcpy(slot + r * n, srcp, n * sizeof(float), kthreads);
+                    e = cudaMemcpyAsync(dstp, slot + r * n, n * sizeof(float), cudaMemcpyHostToDevice, s_up);
+                }
+                if (e == cudaSuccess) e = cudaEventRecord(ev_up[c], s_up);
+                if (e != cudaSuccess) thread_rc.store((int)e);
+                {
+                    std::lock_guard<std::mutex> lk(mu);
+                    up_ready = c + 1;
+                }
+                cv.notify_all();
+            }
+        });
+        t_down = std::thread([&] {  // D2H into a pinned slot, then host threads unpack it while the next D2H runs
+            cudaSetDevice(p->dev);
+            std::vector<cudaEvent_t> evs;
+            DownJob pending{nullptr, 0, 0};
+            int j = 0, pending_slot = 0;
+            auto unpack = [&](const DownJob &d, int slot_i, cudaEvent_t landed) {
+                cudaError_t e = cudaEventSynchronize(landed);
+                if (e != cudaSuccess) {
+                    thread_rc.store((int)e);
+                    return;
+                }
+                const size_t n = (size_t)d.n * plane;
+                const float *slot = static_cast<const float *>(g_staging.dn[slot_i]);
+                for (int r = 0; r < 3; ++r) par_memcpy(h_u + r * lvl + (size_t)d.x0 * plane, slot + r * n, n * sizeof(float), kthreads);
+            };
+            for (;;) {
+                DownJob d;
+                {
+                    std::unique_lock<std::mutex> lk(mu);
+                    cv.wait(lk, [&] { return !jobs.empty() || jobs_closed; });
+                    if (jobs.empty()) break;
+                    d = jobs.front();
+                    jobs.pop_front();
+                }
+                const int slot_i = j & 1;
+                const size_t n = (size_t)d.n * plane;
+                float *slot = static_cast<float *>(g_staging.dn[slot_i]);
+                cudaEvent_t landed = nullptr;
+                cudaError_t e = cudaStreamWaitEvent(s_down, d.after, 0);
+                for (int r = 0; r < 3 && e == cudaSuccess; ++r)
+                    e = cudaMemcpyAsync(slot + r * n, p->d_u + r * lvl + (size_t)d.x0 * plane, n * sizeof(float), cudaMemcpyDeviceToHost, s_down);
+                if (e == cudaSuccess) e = cudaEventCreateWithFlags(&landed, cudaEventDisableTiming);
+                if (e == cudaSuccess) e = cudaEventRecord(landed, s_down);
+                if (e != cudaSuccess) thread_rc.store((int)e);
+                if (landed) evs.push_back(landed);
+                if (pending.n > 0) unpack(pending, pending_slot, evs[evs.size() - 2]);
+                if (e != cudaSuccess) {
+                    pending.n = 0;
+                    break;
+                }
+                pending = d;
+                pending_slot = slot_i;
+                ++j;
+            }
+            if (pending.n > 0 && !evs.empty()) unpack(pending, pending_slot, evs.back());
+            for (cudaEvent_t e : evs) cudaEventDestroy(e);
+        });
+    }
     int uploaded = 0;
     auto upload_through = [&](int c_last) -> int {
+        if (bounce) {  // the packing thread enqueues the copies; wait until chunk c_last is on its way
+            c_last = std::min(c_last, nchunks - 1);
+            std::unique_lock<std::mutex> lk(mu);
+            cv.wait(lk, [&] { return up_ready > c_last || thread_rc.load() != 0; });
+            return thread_rc.load();
+        }
         for (; uploaded <= c_last && uploaded < nchunks; ++uploaded) {
             const size_t x0 = (size_t)uploaded * B, n = std::min<size_t>(B, g.nxp - x0) * plane;
             for (int r = 0; r < 3; ++r)
@@ -1056,7 +1248,14 @@ extern "C" int fdtd_b200_plan_run_staged(fdtd_b200_plan *p, float *h_u, const fl
         STAGED_CHECK(cudaEventRecord(ev_done[b], p->stream));
         // planes below X0 + (b+1)B - 2(T-1) have been through all T steps
         const int fin = b == nblocks - 1 ? g.X1 : std::min(g.X1, g.X0 + (b + 1) * B - 2 * (T - 1));
-        if (fin > downloaded) {
+        if (fin > downloaded && bounce) {
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                jobs.push_back(DownJob{ev_done[b], downloaded, fin - downloaded});
+            }
+            cv.notify_all();
+            downloaded = fin;
+        } else if (fin > downloaded) {
             STAGED_CHECK(cudaStreamWaitEvent(s_down, ev_done[b], 0));
             const size_t n = (size_t)(fin - downloaded) * plane;
             for (int r = 0; r < 3; ++r)
@@ -1066,6 +1265,11 @@ extern "C" int fdtd_b200_plan_run_staged(fdtd_b200_plan *p, float *h_u, const fl
         }
     }
     if (!rc) rc = upload_through(nchunks - 1);  // trailing halo planes (the device copy stays complete for later runs)
+    if (bounce) {
+        if (rc) thread_rc.store(rc);
+        join_threads();  // all chunks are on their way, all finished planes are back in the caller's array
+        if (!rc) rc = thread_rc.load();
+    }
     if (rc) return cleanup(rc);
     if (trace) {
         cudaEventRecord(tl[1], s_up);

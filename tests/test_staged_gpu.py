@@ -19,6 +19,17 @@ def interior_sources(crd, shape):
     return np.clip(crd, np.float32(0.2), hi).astype(np.float32)
 
 
+@pytest.fixture(params=[0, 1], ids=["direct", "bounce"])
+def bounce(request):
+    """numpy arrays are pageable: FDTD_B200_BOUNCE=1 (the default for pageable arrays) packs chunks into pinned
+    buffers with host threads, 0 hands the caller's arrays to cudaMemcpyAsync directly."""
+    import os
+
+    os.environ["FDTD_B200_BOUNCE"] = str(request.param)
+    yield request.param
+    del os.environ["FDTD_B200_BOUNCE"]
+
+
 @pytest.mark.parametrize("shape,T,planes,time_m", [
     ((70, 24, 64), 7, 8, 0),      # several blocks, skew 2(T-1) = 12 > block length
     ((64, 16, 32), 1, 32, 0),     # a single step: exactly two blocks
@@ -26,7 +37,7 @@ def interior_sources(crd, shape):
     ((50, 12, 36), 9, 8, 2),      # generic kernel (small grid)
     ((45, 9, 10), 6, 8, 0),       # nz % 4 != 0: generic kernel only
 ])
-def test_staged_matches_oracle_and_three_phase_path(pkg, oracle, shape, T, planes, time_m):
+def test_staged_matches_oracle_and_three_phase_path(pkg, oracle, bounce, shape, T, planes, time_m):
     rng = np.random.default_rng(sum(shape) + T)
     u, m, src, crd = random_case(rng, shape, time_m + T, 5)
     crd = interior_sources(crd, shape)
@@ -91,7 +102,7 @@ def test_staged_refuses_what_it_cannot_do(pkg, oracle):
     assert rc == 0 and bits_equal(out, ref)
 
 
-def test_abi_takes_the_staged_path_and_matches_golden(pkg, oracle, golden):
+def test_abi_takes_the_staged_path_and_matches_golden(pkg, oracle, golden, bounce):
     """Kernel_CUDA_Optimized on the driver's 256^3 benchmark config: pipelined staging, same bits as the reference
     build, and section0 still covers only the 45 timed steps."""
     import hashlib

@@ -49,7 +49,7 @@ struct Tb2Plan {
     alignas(64) CUtensorMap map_cur;   // u as (z,y,x,level), box (tz+8, ty+8, 1, 1): u^n with the radius-4 halo
     alignas(64) CUtensorMap map_prev;  // u as (z,y,x,level), box (tz+8, ty+4, 1, 1): u^{n-1} on the extended tile
     alignas(64) CUtensorMap map_m;     // m as (z,y,x), box (tz+8, ty+4, 1)
-    int ty, tz, xchunk, variant;       // output tile, x planes per CTA
+    int ty, tz, rows, xchunk, variant;  // output tile, rows per thread, x planes per CTA
     size_t smem_bytes;
     bool valid = false;
 };

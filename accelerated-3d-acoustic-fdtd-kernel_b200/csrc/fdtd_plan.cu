@@ -14,6 +14,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <atomic>
 #include <condition_variable>
 #include <deque>
@@ -219,7 +220,12 @@ extern "C" int fdtd_b200_plan_destroy(fdtd_b200_plan *p)
 {
     if (!p) return 0;
     cudaSetDevice(p->dev);
+    const bool trace = env_int("FDTD_B200_TRACE", 0) > 1;
+    const auto t_a = std::chrono::steady_clock::now();
     plan_free_sources(p);
+    if (trace)
+        fprintf(stderr, "[fdtd_b200] destroy: sources freed after %.2f ms\n",
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_a).count());
     for (int s = 0; s < 2; ++s)
         if (p->ipc_base[s]) cudaIpcCloseMemHandle(p->ipc_base[s]);
     if (p->cache_buffers && p->d_u && p->d_m) {
@@ -586,7 +592,7 @@ extern "C" int fdtd_b200_plan_get_option(fdtd_b200_plan *p, const char *key, int
     if (!strcmp(key, "t_fuse_used")) { *value = p->t_fuse_used; return 0; }
     if (!strcmp(key, "tile_y_used")) { *value = two ? p->tb2.ty : (p->tma.valid ? p->tma.ty : 0); return 0; }
     if (!strcmp(key, "tile_z_used")) { *value = two ? p->tb2.tz : (p->tma.valid ? p->tma.tz : 0); return 0; }
-    if (!strcmp(key, "rows_used")) { *value = two ? 1 : (p->tma.valid ? p->tma.rows : 0); return 0; }
+    if (!strcmp(key, "rows_used")) { *value = two ? p->tb2.rows : (p->tma.valid ? p->tma.rows : 0); return 0; }
     if (!strcmp(key, "stages_used")) { *value = p->tma.valid ? p->tma.stages : 0; return 0; }
     if (!strcmp(key, "xchunk_used")) { *value = two ? p->tb2.xchunk : (p->tma.valid ? p->tma.xchunk : 0); return 0; }
     if (!strcmp(key, "ncells_fused")) { *value = p->ncells_int; return 0; }
@@ -946,23 +952,73 @@ void staging_release()
     g_staging.busy = false;
 }
 
-// memcpy split over k threads (one thread moves ~10 GB/s; the two PCIe directions want ~50 each)
-void par_memcpy(void *dst, const void *src, size_t bytes, int k)
-{
-    if (k <= 1 || bytes < (size_t)(4 << 20)) {
-        memcpy(dst, src, bytes);
-        return;
+// memcpy split over k persistent threads (one thread moves ~10 GB/s; each PCIe direction wants ~50)
+class CopyPool {
+  public:
+    explicit CopyPool(int k)
+    {
+        for (int i = 0; i < k; ++i) th_.emplace_back([this] { work(); });
     }
-    const size_t part = ((bytes + k - 1) / k + 4095) / 4096 * 4096;
-    std::vector<std::thread> th;
-    for (int i = 1; i < k; ++i) {
-        const size_t off = (size_t)i * part;
-        if (off >= bytes) break;
-        th.emplace_back([=] { memcpy((char *)dst + off, (const char *)src + off, std::min(part, bytes - off)); });
+    ~CopyPool()
+    {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            stop_ = true;
+        }
+        cv_.notify_all();
+        for (auto &t : th_) t.join();
     }
-    memcpy(dst, src, std::min(part, bytes));
-    for (auto &t : th) t.join();
-}
+    void copy(void *dst, const void *src, size_t bytes)
+    {
+        const int k = (int)th_.size();
+        if (k <= 1 || bytes < (size_t)(1 << 20)) {
+            memcpy(dst, src, bytes);
+            return;
+        }
+        const size_t part = ((bytes + k - 1) / k + 4095) / 4096 * 4096;
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            for (size_t off = 0; off < bytes; off += part) {
+                q_.push_back(Task{(char *)dst + off, (const char *)src + off, std::min(part, bytes - off)});
+                ++pending_;
+            }
+        }
+        cv_.notify_all();
+        std::unique_lock<std::mutex> lk(mu_);
+        done_.wait(lk, [this] { return pending_ == 0; });
+    }
+
+  private:
+    struct Task {
+        char *d;
+        const char *s;
+        size_t n;
+    };
+    void work()
+    {
+        for (;;) {
+            Task t;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [this] { return stop_ || !q_.empty(); });
+                if (q_.empty()) return;
+                t = q_.front();
+                q_.pop_front();
+            }
+            memcpy(t.d, t.s, t.n);
+            {
+                std::lock_guard<std::mutex> lk(mu_);
+                if (--pending_ == 0) done_.notify_all();
+            }
+        }
+    }
+    std::vector<std::thread> th_;
+    std::mutex mu_;
+    std::condition_variable cv_, done_;
+    std::deque<Task> q_;
+    int pending_ = 0;
+    bool stop_ = false;
+};
 
 bool is_pinned(const void *q)
 {
@@ -1050,8 +1106,13 @@ extern "C" int fdtd_b200_plan_run_staged(fdtd_b200_plan *p, float *h_u, const fl
     const bool bounce = env_int("FDTD_B200_BOUNCE", (is_pinned(h_u) && is_pinned(h_m)) ? 0 : 1) != 0;
     const int kthreads = std::max(1, std::min(env_int("FDTD_B200_COPY_THREADS", 8), (int)std::thread::hardware_concurrency() / 2));
     bool have_staging = false;
+    // the bounce ring moves sub-chunks of Bb planes: slots of ~32 MB (never re-allocated when the grid changes,
+    // unless one plane of the four arrays is larger than that)
+    const int Bb = (int)std::max<size_t>(1, std::min<size_t>(B, ((size_t)32 << 20) / (4 * plane * sizeof(float))));
+    const int nsub = (g.nxp + Bb - 1) / Bb;
     if (bounce) {
-        const int rs = staging_acquire(4 * (size_t)B * plane * sizeof(float), 3 * (size_t)B * plane * sizeof(float));
+        const size_t up_bytes = std::max<size_t>((size_t)32 << 20, 4 * (size_t)Bb * plane * sizeof(float));
+        const int rs = staging_acquire(up_bytes, up_bytes / 4 * 3);
         if (rs) return cleanup(rs == (int)cudaErrorNotReady ? (int)cudaErrorNotSupported : rs);
         have_staging = true;
     }
@@ -1096,19 +1157,20 @@ extern "C" int fdtd_b200_plan_run_staged(fdtd_b200_plan *p, float *h_u, const fl
     }
 
     // upload chunks: padded planes [c*B, (c+1)*B) of u (three levels) and m
-    ev_up.resize(nchunks);
+    ev_up.resize(bounce ? nsub : nchunks);
     if (bounce) {
         for (auto &e : ev_up) STAGED_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-        t_up = std::thread([&] {  // pack a chunk into a pinned slot with host threads, then hand it to the DMA engine
+        t_up = std::thread([&] {  // pack a sub-chunk into a pinned slot with host threads, then hand it to the DMA engine
             cudaSetDevice(p->dev);
-            for (int c = 0; c < nchunks && !thread_rc.load(); ++c) {
-                const size_t x0 = (size_t)c * B, n = std::min<size_t>(B, g.nxp - x0) * plane;
+            CopyPool pool(kthreads);
+            for (int c = 0; c < nsub && !thread_rc.load(); ++c) {
+                const size_t x0 = (size_t)c * Bb, n = std::min<size_t>(Bb, g.nxp - x0) * plane;
                 float *slot = static_cast<float *>(g_staging.up[c % 3]);
-                cudaError_t e = c >= 3 ? cudaEventSynchronize(ev_up[c - 3]) : cudaSuccess;  // the slot's previous chunk has left
+                cudaError_t e = c >= 3 ? cudaEventSynchronize(ev_up[c - 3]) : cudaSuccess;  // the slot's previous sub-chunk has left
                 for (int r = 0; r < 4 && e == cudaSuccess; ++r) {
                     const float *srcp = r < 3 ? h_u + r * lvl + x0 * plane : h_m + x0 * plane;
                     float *dstp = r < 3 ? p->d_u + r * lvl + x0 * plane : p->d_m + x0 * plane;
-                    par_memcpy(slot + r * n, srcp, n * sizeof(float), kthreads);
+                    pool.copy(slot + r * n, srcp, n * sizeof(float));
                     e = cudaMemcpyAsync(dstp, slot + r * n, n * sizeof(float), cudaMemcpyHostToDevice, s_up);
                 }
                 if (e == cudaSuccess) e = cudaEventRecord(ev_up[c], s_up);
@@ -1122,6 +1184,7 @@ extern "C" int fdtd_b200_plan_run_staged(fdtd_b200_plan *p, float *h_u, const fl
         });
         t_down = std::thread([&] {  // D2H into a pinned slot, then host threads unpack it while the next D2H runs
             cudaSetDevice(p->dev);
+            CopyPool pool(kthreads);
             std::vector<cudaEvent_t> evs;
             DownJob pending{nullptr, 0, 0};
             int j = 0, pending_slot = 0;
@@ -1133,7 +1196,7 @@ extern "C" int fdtd_b200_plan_run_staged(fdtd_b200_plan *p, float *h_u, const fl
                 }
                 const size_t n = (size_t)d.n * plane;
                 const float *slot = static_cast<const float *>(g_staging.dn[slot_i]);
-                for (int r = 0; r < 3; ++r) par_memcpy(h_u + r * lvl + (size_t)d.x0 * plane, slot + r * n, n * sizeof(float), kthreads);
+                for (int r = 0; r < 3; ++r) pool.copy(h_u + r * lvl + (size_t)d.x0 * plane, slot + r * n, n * sizeof(float));
             };
             for (;;) {
                 DownJob d;
@@ -1170,8 +1233,8 @@ extern "C" int fdtd_b200_plan_run_staged(fdtd_b200_plan *p, float *h_u, const fl
     }
     int uploaded = 0;
     auto upload_through = [&](int c_last) -> int {
-        if (bounce) {  // the packing thread enqueues the copies; wait until chunk c_last is on its way
-            c_last = std::min(c_last, nchunks - 1);
+        if (bounce) {  // the packing thread enqueues the copies; wait until sub-chunk c_last is on its way
+            c_last = std::min(c_last, nsub - 1);
             std::unique_lock<std::mutex> lk(mu);
             cv.wait(lk, [&] { return up_ready > c_last || thread_rc.load() != 0; });
             return thread_rc.load();
@@ -1199,8 +1262,9 @@ extern "C" int fdtd_b200_plan_run_staged(fdtd_b200_plan *p, float *h_u, const fl
     for (int b = 0; b < nblocks && !rc; ++b) {
         // step 0 of this block reads up to padded plane X0 + (b+1)B + 1
         const int need = std::min(g.nxp - 1, g.X0 + (b + 1) * B + 1);
-        if ((rc = upload_through(need / B))) break;
-        STAGED_CHECK(cudaStreamWaitEvent(p->stream, ev_up[std::min(need / B, nchunks - 1)], 0));
+        const int cdiv = bounce ? Bb : B, clast = (bounce ? nsub : nchunks) - 1;
+        if ((rc = upload_through(need / cdiv))) break;
+        STAGED_CHECK(cudaStreamWaitEvent(p->stream, ev_up[std::min(need / cdiv, clast)], 0));
         bool timing = false;
         for (int s = 0; s < T && !rc; ++s) {
             const int time = time_m + s;
@@ -1251,7 +1315,7 @@ extern "C" int fdtd_b200_plan_run_staged(fdtd_b200_plan *p, float *h_u, const fl
         if (fin > downloaded && bounce) {
             {
                 std::lock_guard<std::mutex> lk(mu);
-                jobs.push_back(DownJob{ev_done[b], downloaded, fin - downloaded});
+                for (int x = downloaded; x < fin; x += Bb) jobs.push_back(DownJob{ev_done[b], x, std::min(Bb, fin - x)});
             }
             cv.notify_all();
             downloaded = fin;
@@ -1264,7 +1328,7 @@ extern "C" int fdtd_b200_plan_run_staged(fdtd_b200_plan *p, float *h_u, const fl
             downloaded = fin;
         }
     }
-    if (!rc) rc = upload_through(nchunks - 1);  // trailing halo planes (the device copy stays complete for later runs)
+    if (!rc) rc = upload_through((bounce ? nsub : nchunks) - 1);  // trailing halo planes (the device copy stays complete for later runs)
     if (bounce) {
         if (rc) thread_rc.store(rc);
         join_threads();  // all chunks are on their way, all finished planes are back in the caller's array

@@ -38,10 +38,12 @@ struct Tb2Args {
     int edge;  // > 0: the first and last chunk are `edge` planes long (slabs with neighbours)
 };
 
-template <int ER, int EC>
+template <int ER, int EC, int RY>
 struct Tb2Shape {
+    static_assert(ER % RY == 0 && (RY == 1 || RY == 2), "rows per thread must divide the extended tile (and its 2-row ghost zone)");
     static constexpr int TY = ER - 4, TZ = 4 * EC - 8;  // output tile
-    static constexpr int NCA = ER * EC;                 // active consumer threads = extended-tile float4 columns
+    static constexpr int TR = ER / RY;                  // thread rows
+    static constexpr int NCA = TR * EC;                 // active consumer threads: RY rows x one float4 column each
     static constexpr int NC = (NCA + 31) / 32 * 32;
     static constexpr int NCW = NC / 32;
     static constexpr int NT = NC + 32;                  // + producer warp
@@ -75,10 +77,26 @@ __device__ __forceinline__ void inject_plane(float4 &r, int X, int Y, int Z, con
     }
 }
 
-template <int ER, int EC, bool EXACT>
-__global__ void __launch_bounds__(Tb2Shape<ER, EC>::NT, 1) stencil_tb2_kernel(const __grid_constant__ Tb2Args a)
+// The four points of one float4 column: c = centre, xm2..xp2 = the same column on the neighbouring planes, ym2..yp2 =
+// the rows above / below, zl / zr = the two floats left / right of the column, u1 = previous time level.
+template <bool EXACT>
+__device__ __forceinline__ float4 column4(const float4 &c, const float4 &xm2, const float4 &xm1, const float4 &xp1,
+                                          const float4 &xp2, const float4 &ym2, const float4 &ym1, const float4 &yp1,
+                                          const float4 &yp2, const float2 &zl, const float2 &zr, const float4 &u1,
+                                          const float4 &m, const Coef &k)
 {
-    using T = Tb2Shape<ER, EC>;
+    float4 o;
+    o.x = point<EXACT>(c.x, xm2.x, xm1.x, xp1.x, xp2.x, ym2.x, ym1.x, yp1.x, yp2.x, zl.x, zl.y, c.y, c.z, u1.x, m.x, k);
+    o.y = point<EXACT>(c.y, xm2.y, xm1.y, xp1.y, xp2.y, ym2.y, ym1.y, yp1.y, yp2.y, zl.y, c.x, c.z, c.w, u1.y, m.y, k);
+    o.z = point<EXACT>(c.z, xm2.z, xm1.z, xp1.z, xp2.z, ym2.z, ym1.z, yp1.z, yp2.z, c.x, c.y, c.w, zr.x, u1.z, m.z, k);
+    o.w = point<EXACT>(c.w, xm2.w, xm1.w, xp1.w, xp2.w, ym2.w, ym1.w, yp1.w, yp2.w, c.y, c.z, zr.x, zr.y, u1.w, m.w, k);
+    return o;
+}
+
+template <int ER, int EC, int RY, bool EXACT>
+__global__ void __launch_bounds__(Tb2Shape<ER, EC, RY>::NT, 1) stencil_tb2_kernel(const __grid_constant__ Tb2Args a)
+{
+    using T = Tb2Shape<ER, EC, RY>;
     constexpr int SU = T::SU, SP = T::SP, SM = T::SM, SB = T::SB, ND = T::ND, HP = T::HP;
     constexpr int USLOT_F = T::USLOT / 4, CSLOT_F = T::CSLOT / 4;
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -162,14 +180,25 @@ __global__ void __launch_bounds__(Tb2Shape<ER, EC>::NT, 1) stencil_tb2_kernel(co
     }
 
     // ---------------------------------------------------------------------- consumers
+    // a thread owns RY consecutive rows x one float4 column of the extended tile
     const bool active = threadIdx.x < T::NCA;
-    const int er = active ? threadIdx.x / EC : 0, ec = active ? threadIdx.x % EC : 0;
+    const int tr = active ? threadIdx.x / EC : 0, ec = active ? threadIdx.x % EC : 0;
+    const int er = tr * RY;  // first row
     const int lane = threadIdx.x & 31;
     const int Y = Yt - 2 + er, Z = Zt - 4 + 4 * ec;
-    const bool inb = active && Y >= g.Y0 && Y < g.Y1 && Z >= g.Z0 && Z < g.Z1;   // interior in (y,z): whole float4
-    const bool core = inb && er >= 2 && er < ER - 2 && ec >= 1 && ec < EC - 1;     // column of the output tile
-    const int ownU = (er + 2) * HP + 4 * ec;  // own column in a u^n slot (rows start at Yt-4)
-    const int ownC = er * HP + 4 * ec;        // own column in a u^{n-1} / m / step-1 slot (rows start at Yt-2)
+    const bool z_in = active && Z >= g.Z0 && Z < g.Z1;                  // interior in z: whole float4
+    const bool rows_core = er >= 2 && er < ER - 2 && ec >= 1 && ec < EC - 1;  // rows of the output tile (2 | RY-aligned)
+    bool inb[RY], core[RY];
+#pragma unroll
+    for (int r = 0; r < RY; ++r) {
+        inb[r] = z_in && Y + r >= g.Y0 && Y + r < g.Y1;  // interior in (y,z)
+        core[r] = inb[r] && rows_core;
+    }
+    bool any_inb = false, any_core = false;
+#pragma unroll
+    for (int r = 0; r < RY; ++r) any_inb |= inb[r], any_core |= core[r];
+    const int ownU = (er + 2) * HP + 4 * ec;  // own first row in a u^n slot (rows start at Yt-4)
+    const int ownC = er * HP + 4 * ec;        // own first row in a u^{n-1} / m / step-1 slot (rows start at Yt-2)
 
     const SourceView &sv = a.s.sv;
     bool chunk_has_src = false;
@@ -179,22 +208,25 @@ __global__ void __launch_bounds__(Tb2Shape<ER, EC>::NT, 1) stencil_tb2_kernel(co
 
     const long long plane = (long long)g.nyp * g.nzp;
     const long long row0 = (long long)Y * g.nzp + Z;
-    float *__restrict__ out1 = a.s.u + (long long)a.s.l_n1 * g.lvl + row0;  // + X*plane
+    float *__restrict__ out1 = a.s.u + (long long)a.s.l_n1 * g.lvl + row0;  // + X*plane + r*nzp
     float *__restrict__ out2 = a.s.u + (long long)a.s.l_n2 * g.lvl + row0;
     // boundary planes also go to the neighbours' ghost planes (peer stores over NVLink): the two outermost
     // planes of u^{n+1} and the four outermost planes of u^{n+2}
     const bool cta_lo = lk.peer_u[0] != nullptr && Xa < g.X0 + 4;
     const bool cta_hi = lk.peer_u[1] != nullptr && Xb > g.X1 - 4;
 
-    // register queues: qU[s % 5] = own column of u^n, stage s (plane Xa-4+s); qR[i % 5] = own step-1 result of
+    // register queues: qU[s % 5][r] = own rows of u^n, stage s (plane Xa-4+s); qR[i % 5][r] = own step-1 results of
     // iteration i (plane Xa-2+i).  The loop is unrolled by 5 so every index is a compile-time constant.
-    float4 qU[5], qR[5];
+    float4 qU[5][RY], qR[5][RY];
 #pragma unroll
-    for (int s = 0; s < 5; ++s) qR[s] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = 0; s < 5; ++s)
+#pragma unroll
+        for (int r = 0; r < RY; ++r) qR[s][r] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
         mbar_wait(full0 + 8 * s, 0);
-        qU[s] = lds128(sU + s * USLOT_F + ownU);
+#pragma unroll
+        for (int r = 0; r < RY; ++r) qU[s][r] = lds128(sU + s * USLOT_F + ownU + r * HP);
         if (s == 1) {  // stages 0 and 1 are never a centre plane: release them now
             __syncwarp();
             if (lane == 0) mbar_arrive(pro0);
@@ -213,56 +245,77 @@ __global__ void __launch_bounds__(Tb2Shape<ER, EC>::NT, 1) stencil_tb2_kernel(co
             // ---------------- step 1: u^{n+1} on plane P1 = Xa-2+i, extended tile
             const int fsl = (k + 4) % 5, csl = (k + 2) % 5;
             mbar_wait(full0 + 8 * fsl, par ^ (uint32_t)((k + 4) / 5));
-            qU[fsl] = lds128(sU + fsl * USLOT_F + ownU);
+#pragma unroll
+            for (int r = 0; r < RY; ++r) qU[fsl][r] = lds128(sU + fsl * USLOT_F + ownU + r * HP);
             const int P1 = Xa - 2 + i;
-            float4 r = qU[csl];  // halo cells keep their value (identical in every level by construction)
-            if (inb && P1 >= XC0 && P1 < XC1) {
+            float4 res[RY];  // halo cells keep their value (identical in every level by construction)
+#pragma unroll
+            for (int r = 0; r < RY; ++r) res[r] = qU[csl][r];
+            if (any_inb && P1 >= XC0 && P1 < XC1) {
                 const float *P = sU + csl * USLOT_F + ownU;
-                const float4 ym2 = lds128(P - 2 * HP), ym1 = lds128(P - HP), yp1 = lds128(P + HP), yp2 = lds128(P + 2 * HP);
-                const float2 zl = lds64(P - 2), zr = lds64(P + 4);
-                const float4 pv = lds128(sP + p3 * CSLOT_F + ownC);
-                const float4 mv = lds128(sM + k * CSLOT_F + ownC);  // m slot (s-4) % 5 = i % 5 = k
-                const float4 c = r, xm2 = qU[k % 5], xm1 = qU[(k + 1) % 5], xp1 = qU[(k + 3) % 5], xp2 = qU[fsl];
-                r.x = point<EXACT>(c.x, xm2.x, xm1.x, xp1.x, xp2.x, ym2.x, ym1.x, yp1.x, yp2.x, zl.x, zl.y, c.y, c.z, pv.x, mv.x, a.s.k);
-                r.y = point<EXACT>(c.y, xm2.y, xm1.y, xp1.y, xp2.y, ym2.y, ym1.y, yp1.y, yp2.y, zl.y, c.x, c.z, c.w, pv.y, mv.y, a.s.k);
-                r.z = point<EXACT>(c.z, xm2.z, xm1.z, xp1.z, xp2.z, ym2.z, ym1.z, yp1.z, yp2.z, c.x, c.y, c.w, zr.x, pv.z, mv.z, a.s.k);
-                r.w = point<EXACT>(c.w, xm2.w, xm1.w, xp1.w, xp2.w, ym2.w, ym1.w, yp1.w, yp2.w, c.y, c.z, zr.x, zr.y, pv.w, mv.w, a.s.k);
-                if (chunk_has_src) inject_plane(r, P1, Y, Z, sv);  // rare: source cells of step n (also in the ghost zone)
-                if (core && P1 >= Xa && P1 < Xb) {
-                    *reinterpret_cast<float4 *>(out1 + (long long)P1 * plane) = r;
-                    if (cta_lo && P1 < g.X0 + 2)
-                        *reinterpret_cast<float4 *>(lk.peer_u[0] + a.s.l_n1 * lk.peer_lvl[0] + (long long)(lk.peer_edge[0] + P1 - g.X0) * plane + row0) = r;
-                    if (cta_hi && P1 >= g.X1 - 2)
-                        *reinterpret_cast<float4 *>(lk.peer_u[1] + a.s.l_n1 * lk.peer_lvl[1] + (long long)(lk.peer_edge[1] + P1 - g.X1) * plane + row0) = r;
+                // this thread's y column on the centre plane: 2 rows above, own rows (registers), 2 rows below
+                float4 col[RY + 4];
+                col[0] = lds128(P - 2 * HP);
+                col[1] = lds128(P - HP);
+                col[RY + 2] = lds128(P + RY * HP);
+                col[RY + 3] = lds128(P + (RY + 1) * HP);
+#pragma unroll
+                for (int r = 0; r < RY; ++r) col[r + 2] = qU[csl][r];
+#pragma unroll
+                for (int r = 0; r < RY; ++r) {
+                    const float2 zl = lds64(P + r * HP - 2), zr = lds64(P + r * HP + 4);
+                    const float4 pv = lds128(sP + p3 * CSLOT_F + ownC + r * HP);
+                    const float4 mv = lds128(sM + k * CSLOT_F + ownC + r * HP);  // m slot (s-4) % 5 = i % 5 = k
+                    float4 v = column4<EXACT>(col[r + 2], qU[k % 5][r], qU[(k + 1) % 5][r], qU[(k + 3) % 5][r], qU[fsl][r], col[r],
+                                              col[r + 1], col[r + 3], col[r + 4], zl, zr, pv, mv, a.s.k);
+                    if (chunk_has_src) inject_plane(v, P1, Y + r, Z, sv);  // rare: source cells of step n (also in the ghost zone)
+                    if (inb[r]) res[r] = v;
+                    if (core[r] && P1 >= Xa && P1 < Xb) {
+                        *reinterpret_cast<float4 *>(out1 + (long long)P1 * plane + r * g.nzp) = v;
+                        if (cta_lo && P1 < g.X0 + 2)
+                            *reinterpret_cast<float4 *>(lk.peer_u[0] + a.s.l_n1 * lk.peer_lvl[0] + (long long)(lk.peer_edge[0] + P1 - g.X0) * plane + row0 + r * g.nzp) = v;
+                        if (cta_hi && P1 >= g.X1 - 2)
+                            *reinterpret_cast<float4 *>(lk.peer_u[1] + a.s.l_n1 * lk.peer_lvl[1] + (long long)(lk.peer_edge[1] + P1 - g.X1) * plane + row0 + r * g.nzp) = v;
+                    }
                 }
             }
-            qR[k % 5] = r;
-            if (active) *reinterpret_cast<float4 *>(sB + b6 * CSLOT_F + ownC) = r;
+#pragma unroll
+            for (int r = 0; r < RY; ++r) {
+                qR[k % 5][r] = res[r];
+                if (active) *reinterpret_cast<float4 *>(sB + b6 * CSLOT_F + ownC + r * HP) = res[r];
+            }
             __syncwarp();
             if (lane == 0) mbar_arrive(bfull0 + 8 * b6);
 
             // ---------------- step 2: u^{n+2} on plane X = Xa+i-4 (centre = step-1 plane of iteration i-2)
             if (i >= 4) {
                 mbar_wait(bfull0 + 8 * b6c, bpar_c);
-                if (core) {
+                if (any_core) {
                     const int X = Xa + i - 4;
                     const float *P = sB + b6c * CSLOT_F + ownC;
-                    const float4 ym2 = lds128(P - 2 * HP), ym1 = lds128(P - HP), yp1 = lds128(P + HP), yp2 = lds128(P + 2 * HP);
-                    const float2 zl = lds64(P - 2), zr = lds64(P + 4);
-                    const float4 mv = lds128(sM + ((k + 3) % 5) * CSLOT_F + ownC);  // m of plane X: slot (i-2) % 5
-                    const float4 c = qR[(k + 3) % 5], xm2 = qR[(k + 1) % 5], xm1 = qR[(k + 2) % 5], xp1 = qR[(k + 4) % 5], xp2 = qR[k % 5];
-                    const float4 pv = qU[k % 5];  // u^n on plane X (stage i): the "previous" level of step 2
-                    float4 o;
-                    o.x = point<EXACT>(c.x, xm2.x, xm1.x, xp1.x, xp2.x, ym2.x, ym1.x, yp1.x, yp2.x, zl.x, zl.y, c.y, c.z, pv.x, mv.x, a.s.k);
-                    o.y = point<EXACT>(c.y, xm2.y, xm1.y, xp1.y, xp2.y, ym2.y, ym1.y, yp1.y, yp2.y, zl.y, c.x, c.z, c.w, pv.y, mv.y, a.s.k);
-                    o.z = point<EXACT>(c.z, xm2.z, xm1.z, xp1.z, xp2.z, ym2.z, ym1.z, yp1.z, yp2.z, c.x, c.y, c.w, zr.x, pv.z, mv.z, a.s.k);
-                    o.w = point<EXACT>(c.w, xm2.w, xm1.w, xp1.w, xp2.w, ym2.w, ym1.w, yp1.w, yp2.w, c.y, c.z, zr.x, zr.y, pv.w, mv.w, a.s.k);
-                    if (chunk_has_src) inject_plane(o, X, Y, Z, sv2);  // source cells of step n+1
-                    *reinterpret_cast<float4 *>(out2 + (long long)X * plane) = o;
-                    if (cta_lo && X < g.X0 + 4)
-                        *reinterpret_cast<float4 *>(lk.peer_u[0] + a.s.l_n2 * lk.peer_lvl[0] + (long long)(lk.peer_edge[0] + X - g.X0) * plane + row0) = o;
-                    if (cta_hi && X >= g.X1 - 4)
-                        *reinterpret_cast<float4 *>(lk.peer_u[1] + a.s.l_n2 * lk.peer_lvl[1] + (long long)(lk.peer_edge[1] + X - g.X1) * plane + row0) = o;
+                    float4 col[RY + 4];
+                    col[0] = lds128(P - 2 * HP);
+                    col[1] = lds128(P - HP);
+                    col[RY + 2] = lds128(P + RY * HP);
+                    col[RY + 3] = lds128(P + (RY + 1) * HP);
+#pragma unroll
+                    for (int r = 0; r < RY; ++r) col[r + 2] = qR[(k + 3) % 5][r];
+#pragma unroll
+                    for (int r = 0; r < RY; ++r) {
+                        const float2 zl = lds64(P + r * HP - 2), zr = lds64(P + r * HP + 4);
+                        const float4 mv = lds128(sM + ((k + 3) % 5) * CSLOT_F + ownC + r * HP);  // m of plane X: slot (i-2) % 5
+                        // x neighbours and centre from the step-1 queue; "previous" level = u^n on this plane (stage i)
+                        float4 o = column4<EXACT>(col[r + 2], qR[(k + 1) % 5][r], qR[(k + 2) % 5][r], qR[(k + 4) % 5][r], qR[k % 5][r], col[r],
+                                                  col[r + 1], col[r + 3], col[r + 4], zl, zr, qU[k % 5][r], mv, a.s.k);
+                        if (chunk_has_src) inject_plane(o, X, Y + r, Z, sv2);  // source cells of step n+1
+                        if (core[r]) {
+                            *reinterpret_cast<float4 *>(out2 + (long long)X * plane + r * g.nzp) = o;
+                            if (cta_lo && X < g.X0 + 4)
+                                *reinterpret_cast<float4 *>(lk.peer_u[0] + a.s.l_n2 * lk.peer_lvl[0] + (long long)(lk.peer_edge[0] + X - g.X0) * plane + row0 + r * g.nzp) = o;
+                            if (cta_hi && X >= g.X1 - 4)
+                                *reinterpret_cast<float4 *>(lk.peer_u[1] + a.s.l_n2 * lk.peer_lvl[1] + (long long)(lk.peer_edge[1] + X - g.X1) * plane + row0 + r * g.nzp) = o;
+                        }
+                    }
                 }
             }
             __syncwarp();
@@ -346,20 +399,25 @@ int launch_shell_copy(float *u, const Grid &g, int from, int to, cudaStream_t st
 // ---------------------------------------------------------------------------- host side
 typedef void (*Tb2KernelFn)(const Tb2Args);
 struct Tb2Variant {
-    int er, ec;
+    int er, ec, rows;
     bool exact;
     Tb2KernelFn fn;
     int nt;
     size_t smem;
 };
-#define FDTD_TB2_1(ER_, EC_, EX_) {ER_, EC_, EX_, stencil_tb2_kernel<ER_, EC_, EX_>, Tb2Shape<ER_, EC_>::NT, (size_t)Tb2Shape<ER_, EC_>::SMEM}
-#define FDTD_TB2(ER_, EC_) FDTD_TB2_1(ER_, EC_, false), FDTD_TB2_1(ER_, EC_, true)
+#define FDTD_TB2_1(ER_, EC_, RY_, EX_) \
+    {ER_, EC_, RY_, EX_, stencil_tb2_kernel<ER_, EC_, RY_, EX_>, Tb2Shape<ER_, EC_, RY_>::NT, (size_t)Tb2Shape<ER_, EC_, RY_>::SMEM}
+#define FDTD_TB2(ER_, EC_, RY_) FDTD_TB2_1(ER_, EC_, RY_, false), FDTD_TB2_1(ER_, EC_, RY_, true)
 static const Tb2Variant g_tb2[] = {
-    // extended tile (rows, float4 columns) -> output tile (ER-4) x (4*EC-8); first match of (ty, tz) wins
-    FDTD_TB2(36, 18),  // 32 x 64
-    FDTD_TB2(32, 18),  // 28 x 64
-    FDTD_TB2(20, 34),  // 16 x 128
-    FDTD_TB2(20, 18),  // 16 x 64
+    // extended tile (rows, float4 columns), rows per thread -> output tile (ER-4) x (4*EC-8); first match wins.
+    // Two rows per thread halve the barrier / address work per point but leave 12 warps per SM instead of 22: the
+    // loop is latency-bound and runs 25% slower (profiles/r01_sweep512_twostep_rows.txt) -- kept for the record.
+    FDTD_TB2(36, 18, 1),  // 32 x 64
+    FDTD_TB2(32, 18, 1),  // 28 x 64
+    FDTD_TB2(20, 34, 1),  // 16 x 128
+    FDTD_TB2(20, 18, 1),  // 16 x 64
+    FDTD_TB2(36, 18, 2),
+    FDTD_TB2(20, 34, 2),
 };
 static const int g_ntb2 = (int)(sizeof(g_tb2) / sizeof(g_tb2[0]));
 
@@ -370,7 +428,8 @@ int tb2_plan_build(Tb2Plan &p, float *u, const float *m, const Grid &g, const Tm
     const int ny = g.Y1 - g.Y0, nz = g.Z1 - g.Z0, nx = g.X1 - g.X0;
     int vi = -1;
     for (int i = 0; i < g_ntb2 && vi < 0; ++i)
-        if (g_tb2[i].exact == exact && (cfg.ty <= 0 || g_tb2[i].er - 4 == cfg.ty) && (cfg.tz <= 0 || 4 * g_tb2[i].ec - 8 == cfg.tz))
+        if (g_tb2[i].exact == exact && (cfg.ty <= 0 || g_tb2[i].er - 4 == cfg.ty) && (cfg.tz <= 0 || 4 * g_tb2[i].ec - 8 == cfg.tz) &&
+            (cfg.rows <= 0 || g_tb2[i].rows == cfg.rows))
             vi = i;
     if (vi < 0) return (int)cudaErrorInvalidValue;
     const Tb2Variant &v = g_tb2[vi];
@@ -405,6 +464,7 @@ int tb2_plan_build(Tb2Plan &p, float *u, const float *m, const Grid &g, const Tm
     }
     p.ty = ty;
     p.tz = tz;
+    p.rows = v.rows;
     p.xchunk = xchunk;
     p.variant = vi;
     p.smem_bytes = v.smem;

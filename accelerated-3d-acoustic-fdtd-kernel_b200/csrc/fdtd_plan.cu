@@ -173,7 +173,6 @@ int fdtd::plan_create_internal(const PlanShape &s, fdtd_b200_plan **out, bool ca
     p->opt_kernel = env_int("FDTD_B200_KERNEL", 0);
     p->opt_exact = env_int("FDTD_B200_EXACT", 1);
     p->opt_fuse = env_int("FDTD_B200_FUSE_INJECT", 1);
-    p->opt_graph = env_int("FDTD_B200_GRAPH", 0);
     p->cfg.ty = env_int("FDTD_B200_TILE_Y", 0);
     p->cfg.tz = env_int("FDTD_B200_TILE_Z", 0);
     p->cfg.rows = env_int("FDTD_B200_ROWS", 0);
@@ -562,7 +561,6 @@ static int *option_slot(fdtd_b200_plan *p, const char *key)
     if (!strcmp(key, "kernel")) return &p->opt_kernel;
     if (!strcmp(key, "exact")) return &p->opt_exact;
     if (!strcmp(key, "fuse_inject")) return &p->opt_fuse;
-    if (!strcmp(key, "graph")) return &p->opt_graph;
     if (!strcmp(key, "t_fuse")) return &p->opt_t_fuse;
     if (!strcmp(key, "tile_y")) return &p->cfg.ty;
     if (!strcmp(key, "tile_z")) return &p->cfg.tz;

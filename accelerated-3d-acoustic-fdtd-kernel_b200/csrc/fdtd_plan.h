@@ -54,7 +54,7 @@ struct fdtd_b200_plan {
     std::vector<long long> h_base_idx;  // host copy of d_base_idx (the staged run gathers mbase from the host's m)
 
     // options
-    int opt_kernel = 0, opt_exact = 1, opt_fuse = 1, opt_graph = 0, opt_t_fuse = 1;
+    int opt_kernel = 0, opt_exact = 1, opt_fuse = 1, opt_t_fuse = 1;
     int opt_stage_planes = -1;       // x planes per block of the staged (pipelined H2D / compute / D2H) run; -1 = auto, 0 = off
     fdtd::TmaConfig cfg{};
     fdtd::TmaPlan tma{};

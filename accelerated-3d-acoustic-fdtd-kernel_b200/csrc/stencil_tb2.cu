@@ -244,7 +244,11 @@ __global__ void __launch_bounds__(Tb2Shape<ER, EC, RY>::NT, 1) stencil_tb2_kerne
             if (i >= nit) break;
             // ---------------- step 1: u^{n+1} on plane P1 = Xa-2+i, extended tile
             const int fsl = (k + 4) % 5, csl = (k + 2) % 5;
+            // both waits first: the two steps of an iteration are independent instruction streams (step 2 works on
+            // the step-1 plane of iteration i-2), so with no barrier operation between them their shared-memory
+            // loads and arithmetic overlap
             mbar_wait(full0 + 8 * fsl, par ^ (uint32_t)((k + 4) / 5));
+            if (i >= 4) mbar_wait(bfull0 + 8 * b6c, bpar_c);
 #pragma unroll
             for (int r = 0; r < RY; ++r) qU[fsl][r] = lds128(sU + fsl * USLOT_F + ownU + r * HP);
             const int P1 = Xa - 2 + i;
@@ -284,12 +288,9 @@ __global__ void __launch_bounds__(Tb2Shape<ER, EC, RY>::NT, 1) stencil_tb2_kerne
                 qR[k % 5][r] = res[r];
                 if (active) *reinterpret_cast<float4 *>(sB + b6 * CSLOT_F + ownC + r * HP) = res[r];
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bfull0 + 8 * b6);
 
             // ---------------- step 2: u^{n+2} on plane X = Xa+i-4 (centre = step-1 plane of iteration i-2)
             if (i >= 4) {
-                mbar_wait(bfull0 + 8 * b6c, bpar_c);
                 if (any_core) {
                     const int X = Xa + i - 4;
                     const float *P = sB + b6c * CSLOT_F + ownC;
@@ -319,7 +320,10 @@ __global__ void __launch_bounds__(Tb2Shape<ER, EC, RY>::NT, 1) stencil_tb2_kerne
                 }
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(done0 + 8 * d8);  // iteration i done: u^n stage i+2, u^{n-1} and m slots reusable
+            if (lane == 0) {
+                mbar_arrive(bfull0 + 8 * b6);  // this warp's part of step-1 plane i is in shared memory
+                mbar_arrive(done0 + 8 * d8);   // iteration i done: u^n stage i+2, u^{n-1} and m slots reusable
+            }
 
             if (++p3 == SP) p3 = 0;
             if (++b6 == SB) b6 = 0;
@@ -426,9 +430,13 @@ int tb2_plan_build(Tb2Plan &p, float *u, const float *m, const Grid &g, const Tm
     p.valid = false;
     if (!tma_supported(g)) return (int)cudaErrorInvalidValue;
     const int ny = g.Y1 - g.Y0, nz = g.Z1 - g.Z0, nx = g.X1 - g.X0;
+    // tile: explicit, or 16 x 128 where it divides the grid (measured 1% ahead of 32 x 64 at 512^3: longer rows per
+    // TMA box), else 32 x 64
+    int want_ty = cfg.ty, want_tz = cfg.tz;
+    if (want_ty <= 0 && want_tz <= 0 && ny % 16 == 0 && nz % 128 == 0) want_ty = 16, want_tz = 128;
     int vi = -1;
     for (int i = 0; i < g_ntb2 && vi < 0; ++i)
-        if (g_tb2[i].exact == exact && (cfg.ty <= 0 || g_tb2[i].er - 4 == cfg.ty) && (cfg.tz <= 0 || 4 * g_tb2[i].ec - 8 == cfg.tz) &&
+        if (g_tb2[i].exact == exact && (want_ty <= 0 || g_tb2[i].er - 4 == want_ty) && (want_tz <= 0 || 4 * g_tb2[i].ec - 8 == want_tz) &&
             (cfg.rows <= 0 || g_tb2[i].rows == cfg.rows))
             vi = i;
     if (vi < 0) return (int)cudaErrorInvalidValue;

@@ -290,6 +290,35 @@ def run_b200_arm(a):
                        if int(os.environ.get("FDTD_B200_STAGE_PLANES", "-1")) != 0 else "three phases (H2D, run, D2H)"}
         del u_h, m_h
 
+    # ---- e2e at N > 1: every rank stages its own slab through the plan API (upload from pinned host memory, the
+    # linked run, download), wall clock bracketed by barriers, max over ranks.  Slabs keep the three-phase order (the
+    # skewed pipeline of the single-GPU path would have to interleave with the neighbours' ghost planes).
+    if world > 1 and not a.no_e2e:
+        nxl = nx_local + 8
+        u_h = torch.zeros((3, nxl, n + 8, n + 8), dtype=torch.float32).pin_memory().numpy()
+        m_h = torch.full((nxl, n + 8, n + 8), 1.5, dtype=torch.float32).pin_memory().numpy()
+        e2e_t = []
+        for i in range(1 + a.e2e_reps):
+            u_h[...] = 0
+            barrier()
+            t0 = time.perf_counter()
+            plan.upload(u_h, m_h)
+            dist.barrier()  # a neighbour's first pass already writes ghost planes into this slab
+            from_slab.run(0, T - 1)
+            plan.download(u_h)
+            barrier()
+            if i > 0:
+                e2e_t.append(time.perf_counter() - t0)
+        tt = torch.tensor([sum(e2e_t) / len(e2e_t)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_s = float(tt.item())
+        line["e2e"] = {"value": pts_per_step * T / e2e_s / 1e9, "unit": "Gpts/s",
+                       "h2d_bytes_per_step": world * (4 * nxl * (n + 8) ** 2 * 4) + src.nbytes + crd.nbytes,
+                       "d2h_bytes_per_step": world * 3 * nxl * (n + 8) ** 2 * 4, "seconds_per_call": e2e_s,
+                       "api": "SlabRun: plan.upload + linked run + plan.download per rank, pinned host buffers",
+                       "arithmetic": arith, "time_steps_per_launch": t_fuse_used, "staging": "three phases (H2D, run, D2H)"}
+        del u_h, m_h
+
     # ---- CPU baseline: the reference's OpenACC source on this box's host cores (bounded sample)
     if world == 1 and rank == 0 and not a.no_cpu and not a.workload:
         plan.close()

@@ -181,6 +181,8 @@ def run_b200_arm(a):
             return from_slab.run(0, T - 1)
         return plan.run(0, T - 1)
 
+    passes = []  # (wall, section0, section1) seconds of every timed operator pass on this rank
+
     def measure(steps, warmup):
         """W untimed + K timed operator passes; device seconds (section timers = CUDA events on the compute
         stream), wall seconds bracketed by barrier + synchronize, max over ranks."""
@@ -190,10 +192,12 @@ def run_b200_arm(a):
         dev_s, kern_s, launches = 0.0, 0.0, 0
         t0 = time.perf_counter()
         for _ in range(steps):
+            tp = time.perf_counter()
             t = one_step()
             dev_s += t.section0 + t.section1
             kern_s += plan.last_kernel_seconds
             launches += plan.last_launches + 2  # + the two fill kernels
+            passes.append((time.perf_counter() - tp, t.section0, t.section1))
         barrier()
         wall = time.perf_counter() - t0
         if world > 1:
@@ -204,6 +208,7 @@ def run_b200_arm(a):
 
     with ClockSampler(local) as clk:
         dev_s, wall, kern_s, launches = measure(a.steps, a.warmup)
+    headline_passes = list(passes)
     pts_per_step = float(nxg) * n * n
     value = pts_per_step * timed_steps * a.steps / dev_s / 1e9
     peak, peak_kind = measured_peak()
@@ -326,6 +331,20 @@ def run_b200_arm(a):
         cb.pop("seconds")
         line["cpu_baseline"] = cb
 
+    if rank == 0 and a.csv:
+        # one row in the reference's benchmark.csv schema (main.cpp:201-249) for harnesses that bypass main.cpp
+        # (SURVEY 8b): mean and POPULATION std over the timed passes, the driver's 36 flop / 64 B per point models
+        # (main.cpp:129-146) over ALL T steps divided by the device time of the timed ones (main.cpp:404,430)
+        def stat(v):
+            v = np.asarray(v, np.float64)
+            return float(v.mean()), float(v.std())
+
+        tot, s0, s1 = (np.array([p[i] for p in headline_passes]) for i in range(3))
+        dev = s0 + s1
+        gf, gb = pts_per_step * T * 36 / dev / 1e9, pts_per_step * T * 64 / dev / 1e9
+        pkg.write_benchmark_csv(a.csv, f"B200_{world}gpu_t{t_fuse_used}", stat(tot), stat(s0), stat(s1), stat(dev),
+                                stat(np.maximum(0.0, tot - dev)), stat(gf), stat(gb), 148 * 128 * 2 * 1.965 * world, peak * world,
+                                36.0 / 64.0, nxg, n, n, T, S)
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -348,6 +367,7 @@ def main():
     ap.add_argument("--exact", type=int, default=0, help="1 = bit-exact arithmetic (0 ulp vs the reference built for the host), "
                     "0 = contracted (FMA, rel L2 ~1e-6; tolerance 1e-4)")
     ap.add_argument("--tfuse", type=int, default=2, help="time steps per launch: 2 = two-step passes (temporal blocking), 1 = one")
+    ap.add_argument("--csv", default="", help="append one row in the reference's benchmark.csv schema to this file")
     ap.add_argument("--no-modes", action="store_true", help="skip the short runs of the other arithmetic / t_fuse modes")
     ap.add_argument("--kernel", type=int, default=None)
     ap.add_argument("--no-e2e", action="store_true")

@@ -76,16 +76,41 @@ extern "C" int fdtd_b200_source_table(const float coord[3], const float o[3], co
 }
 
 // ---------------------------------------------------------------------------- plan life cycle
+// Small per-plan device arrays (source table, src rows) come out of a 2 MB arena in the tail of the u allocation
+// instead of eight cudaMalloc / cudaFree pairs per Kernel_* call: on the pool's boxes a cudaFree can take 100+ ms.
+static constexpr size_t kArenaBytes = (size_t)2 << 20;
+
+static bool in_arena(const fdtd_b200_plan *p, const void *q)
+{
+    const char *c = static_cast<const char *>(q), *a = reinterpret_cast<const char *>(p->d_u) + p->arena_offset;
+    return q && c >= a && c < a + kArenaBytes;
+}
+static void small_free(fdtd_b200_plan *p, void *q)
+{
+    if (q && !in_arena(p, q)) cudaFree(q);
+}
+template <class T>
+static cudaError_t small_alloc(fdtd_b200_plan *p, T **out, size_t bytes)
+{
+    const size_t need = (bytes + 255) / 256 * 256;
+    if (p->arena_used + need <= kArenaBytes) {
+        *out = reinterpret_cast<T *>(reinterpret_cast<char *>(p->d_u) + p->arena_offset + p->arena_used);
+        p->arena_used += need;
+        return cudaSuccess;
+    }
+    return cudaMalloc(out, bytes);
+}
+
 static void plan_free_sources(fdtd_b200_plan *p)
 {
-    cudaFree(p->d_src);
-    cudaFree(p->d_cells);
-    cudaFree(p->d_contribs);
-    cudaFree(p->d_plane_off);
-    cudaFree(p->d_mbase);
-    cudaFree(p->d_base_idx);
-    cudaFree(p->d_cells2);
-    cudaFree(p->d_plane_off2);
+    small_free(p, p->d_src);
+    small_free(p, p->d_cells);
+    small_free(p, p->d_contribs);
+    small_free(p, p->d_plane_off);
+    small_free(p, p->d_mbase);
+    small_free(p, p->d_base_idx);
+    small_free(p, p->d_cells2);
+    small_free(p, p->d_plane_off2);
     p->d_cells2 = nullptr;
     p->d_plane_off2 = nullptr;
     p->ncells2 = 0;
@@ -96,6 +121,7 @@ static void plan_free_sources(fdtd_b200_plan *p)
     p->d_plane_off = nullptr;
     p->d_mbase = nullptr;
     p->d_base_idx = nullptr;
+    p->arena_used = 0;
     p->h_base_idx.clear();
     p->ncells_int = p->ncells_halo = p->ncells_all = 0;
     p->n_mbase = 0;
@@ -183,7 +209,8 @@ int fdtd::plan_create_internal(const PlanShape &s, fdtd_b200_plan **out, bool ca
 
     cudaError_t e = cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking);
     p->flags_offset = (FDTD_LEVELS * (size_t)p->g.lvl * sizeof(float) + 255) / 256 * 256;
-    p->u_bytes = p->flags_offset + 256;
+    p->arena_offset = p->flags_offset + 256;
+    p->u_bytes = p->arena_offset + kArenaBytes;
     p->m_bytes = (size_t)p->g.lvl * sizeof(float);
     const char *nc = getenv("FDTD_B200_NO_CACHE");
     p->cache_buffers = cache_buffers && !(nc && *nc == '1');
@@ -525,30 +552,30 @@ extern "C" int fdtd_b200_plan_set_sources(fdtd_b200_plan *p, const float *src, i
     p->src_size0 = src_size0;
     p->pstride = pstride;
     p->n_mbase = p_src_M + 1;
-    FDTD_CHECK(cudaMalloc(&p->d_src, (size_t)src_size0 * pstride * sizeof(float)));
+    FDTD_CHECK(small_alloc(p, &p->d_src, (size_t)src_size0 * pstride * sizeof(float)));
     FDTD_CHECK(cudaMemcpy(p->d_src, src, (size_t)src_size0 * pstride * sizeof(float), cudaMemcpyHostToDevice));
-    FDTD_CHECK(cudaMalloc(&p->d_plane_off, plane_off.size() * sizeof(int)));
+    FDTD_CHECK(small_alloc(p, &p->d_plane_off, plane_off.size() * sizeof(int)));
     FDTD_CHECK(cudaMemcpy(p->d_plane_off, plane_off.data(), plane_off.size() * sizeof(int), cudaMemcpyHostToDevice));
-    FDTD_CHECK(cudaMalloc(&p->d_mbase, (size_t)p->n_mbase * sizeof(float)));
-    FDTD_CHECK(cudaMalloc(&p->d_base_idx, (size_t)p->n_mbase * sizeof(long long)));
+    FDTD_CHECK(small_alloc(p, &p->d_mbase, (size_t)p->n_mbase * sizeof(float)));
+    FDTD_CHECK(small_alloc(p, &p->d_base_idx, (size_t)p->n_mbase * sizeof(long long)));
     FDTD_CHECK(cudaMemcpy(p->d_base_idx, base_idx.data(), (size_t)p->n_mbase * sizeof(long long), cudaMemcpyHostToDevice));
     p->src_halo_global = tab.halo_global;
     p->h_base_idx = base_idx;
     p->ncells2 = (int)tab.cells2.size();
     if (!tab.cells2.empty()) {
-        FDTD_CHECK(cudaMalloc(&p->d_cells2, tab.cells2.size() * sizeof(SourceCell)));
+        FDTD_CHECK(small_alloc(p, &p->d_cells2, tab.cells2.size() * sizeof(SourceCell)));
         FDTD_CHECK(cudaMemcpy(p->d_cells2, tab.cells2.data(), tab.cells2.size() * sizeof(SourceCell), cudaMemcpyHostToDevice));
-        FDTD_CHECK(cudaMalloc(&p->d_plane_off2, tab.plane_off2.size() * sizeof(int)));
+        FDTD_CHECK(small_alloc(p, &p->d_plane_off2, tab.plane_off2.size() * sizeof(int)));
         FDTD_CHECK(cudaMemcpy(p->d_plane_off2, tab.plane_off2.data(), tab.plane_off2.size() * sizeof(int), cudaMemcpyHostToDevice));
     }
     if (!contribs.empty() && all.empty()) {  // only ghost cells: the contribution list is still needed
-        FDTD_CHECK(cudaMalloc(&p->d_contribs, contribs.size() * sizeof(SourceContrib)));
+        FDTD_CHECK(small_alloc(p, &p->d_contribs, contribs.size() * sizeof(SourceContrib)));
         FDTD_CHECK(cudaMemcpy(p->d_contribs, contribs.data(), contribs.size() * sizeof(SourceContrib), cudaMemcpyHostToDevice));
     }
     if (!all.empty()) {
-        FDTD_CHECK(cudaMalloc(&p->d_cells, all.size() * sizeof(SourceCell)));
+        FDTD_CHECK(small_alloc(p, &p->d_cells, all.size() * sizeof(SourceCell)));
         FDTD_CHECK(cudaMemcpy(p->d_cells, all.data(), all.size() * sizeof(SourceCell), cudaMemcpyHostToDevice));
-        FDTD_CHECK(cudaMalloc(&p->d_contribs, contribs.size() * sizeof(SourceContrib)));
+        FDTD_CHECK(small_alloc(p, &p->d_contribs, contribs.size() * sizeof(SourceContrib)));
         FDTD_CHECK(cudaMemcpy(p->d_contribs, contribs.data(), contribs.size() * sizeof(SourceContrib), cudaMemcpyHostToDevice));
     }
     return 0;

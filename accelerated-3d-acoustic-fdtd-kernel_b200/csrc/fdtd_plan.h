@@ -73,6 +73,7 @@ struct fdtd_b200_plan {
     // x-slab neighbours: flag words live in the tail of the u allocation (one IPC handle covers both)
     int *d_flags = nullptr;          // [0] ready-from-lower, [1] ready-from-upper, [2..3] CTA counters, [4] error
     size_t flags_offset = 0;         // byte offset of d_flags inside the u allocation
+    size_t arena_offset = 0, arena_used = 0;  // small-array arena behind the flag words (fdtd_plan.cu)
     fdtd::SlabLink link{};           // peers (null = physical boundary)
     void *ipc_base[2] = {nullptr, nullptr};  // mappings opened with cudaIpcOpenMemHandle
     int epoch = 0;                   // step sequence number, identical on every slab

@@ -22,6 +22,13 @@ struct PlanShape {
 // more than the 50 time steps).
 int plan_create_internal(const PlanShape &s, fdtd_b200_plan **out, bool cache_buffers = false);
 
+// shared between fdtd_plan.cu and fdtd_staged.cu
+int env_int(const char *key, int fallback);
+// kernel choice, tensor maps, two-step feasibility, mbase gather: what every run does before its first launch
+int plan_prepare(fdtd_b200_plan *p);
+// ring level r lives in device level r again (after an upload / fill); shell_state: 0 unknown, 1 identical shells
+void reset_placement(fdtd_b200_plan *p, int shell_state);
+
 }  // namespace fdtd
 
 struct fdtd_b200_plan {

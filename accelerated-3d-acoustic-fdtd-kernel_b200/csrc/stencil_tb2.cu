@@ -77,22 +77,6 @@ __device__ __forceinline__ void inject_plane(float4 &r, int X, int Y, int Z, con
     }
 }
 
-// The four points of one float4 column: c = centre, xm2..xp2 = the same column on the neighbouring planes, ym2..yp2 =
-// the rows above / below, zl / zr = the two floats left / right of the column, u1 = previous time level.
-template <bool EXACT>
-__device__ __forceinline__ float4 column4(const float4 &c, const float4 &xm2, const float4 &xm1, const float4 &xp1,
-                                          const float4 &xp2, const float4 &ym2, const float4 &ym1, const float4 &yp1,
-                                          const float4 &yp2, const float2 &zl, const float2 &zr, const float4 &u1,
-                                          const float4 &m, const Coef &k)
-{
-    float4 o;
-    o.x = point<EXACT>(c.x, xm2.x, xm1.x, xp1.x, xp2.x, ym2.x, ym1.x, yp1.x, yp2.x, zl.x, zl.y, c.y, c.z, u1.x, m.x, k);
-    o.y = point<EXACT>(c.y, xm2.y, xm1.y, xp1.y, xp2.y, ym2.y, ym1.y, yp1.y, yp2.y, zl.y, c.x, c.z, c.w, u1.y, m.y, k);
-    o.z = point<EXACT>(c.z, xm2.z, xm1.z, xp1.z, xp2.z, ym2.z, ym1.z, yp1.z, yp2.z, c.x, c.y, c.w, zr.x, u1.z, m.z, k);
-    o.w = point<EXACT>(c.w, xm2.w, xm1.w, xp1.w, xp2.w, ym2.w, ym1.w, yp1.w, yp2.w, c.y, c.z, zr.x, zr.y, u1.w, m.w, k);
-    return o;
-}
-
 template <int ER, int EC, int RY, bool EXACT>
 __global__ void __launch_bounds__(Tb2Shape<ER, EC, RY>::NT, 1) stencil_tb2_kernel(const __grid_constant__ Tb2Args a)
 {

@@ -222,10 +222,7 @@ __global__ void __launch_bounds__(TileShape<TY, TZ, RY, NS>::NT, MINB)
                 const float4 c = col[r + 2];
                 const float4 xm2 = q[k % 5][r], xm1 = q[(k + 1) % 5][r], xp1 = q[(k + 3) % 5][r], xp2 = q[(k + 4) % 5][r];
                 const float4 ym2 = col[r], ym1 = col[r + 1], yp1 = col[r + 3], yp2 = col[r + 4];
-                o[r].x = point<EXACT>(c.x, xm2.x, xm1.x, xp1.x, xp2.x, ym2.x, ym1.x, yp1.x, yp2.x, zl[r].x, zl[r].y, c.y, c.z, u1v[r].x, mv[r].x, a.s.k);
-                o[r].y = point<EXACT>(c.y, xm2.y, xm1.y, xp1.y, xp2.y, ym2.y, ym1.y, yp1.y, yp2.y, zl[r].y, c.x, c.z, c.w, u1v[r].y, mv[r].y, a.s.k);
-                o[r].z = point<EXACT>(c.z, xm2.z, xm1.z, xp1.z, xp2.z, ym2.z, ym1.z, yp1.z, yp2.z, c.x, c.y, c.w, zr[r].x, u1v[r].z, mv[r].z, a.s.k);
-                o[r].w = point<EXACT>(c.w, xm2.w, xm1.w, xp1.w, xp2.w, ym2.w, ym1.w, yp1.w, yp2.w, c.y, c.z, zr[r].x, zr[r].y, u1v[r].w, mv[r].w, a.s.k);
+                o[r] = column4<EXACT>(c, xm2, xm1, xp1, xp2, ym2, ym1, yp1, yp2, zl[r], zr[r], u1v[r], mv[r], a.s.k);
             }
 
             if (chunk_has_src) {  // fused Section1: rare path, only chunks that contain a source cell

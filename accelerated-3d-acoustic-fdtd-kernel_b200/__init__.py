@@ -9,6 +9,7 @@ but every compute call goes to the CUDA library and raises if it cannot run.
 from .host import (  # noqa: F401
     HALO,
     WARMUP_STEPS,
+    Checksum,
     Dataobj,
     FdtdError,
     Geometry,

@@ -15,14 +15,8 @@
 
 #include <algorithm>
 #include <chrono>
-#include <atomic>
-#include <condition_variable>
-#include <deque>
-#include <functional>
-#include <fstream>
 #include <map>
 #include <mutex>
-#include <thread>
 #include <tuple>
 #include <vector>
 
@@ -647,7 +641,10 @@ static int plan_step(fdtd_b200_plan *p, int time, bool first_of_run, Mark &&mark
     a.t0 = p->phys[t0];  // device levels that hold the ring levels
     a.t1 = p->phys[t1];
     a.t2 = p->phys[t2];
-    const bool fuse = has_src && p->opt_fuse && p->ncells_int > 0;
+    // linked slabs always fuse: the boundary planes leave for the neighbour's ghost planes inside the Section0
+    // launch, so a source cell on them must already be in (a scatter afterwards would never reach the neighbour)
+    const bool linked = p->link.peer_u[0] || p->link.peer_u[1];
+    const bool fuse = has_src && (p->opt_fuse || linked) && p->ncells_int > 0;
     if (fuse) {
         a.sv.plane_off = p->d_plane_off;
         a.sv.cells = p->d_cells;
@@ -720,9 +717,11 @@ static int plan_pass2(fdtd_b200_plan *p, int time, bool first_of_run)
 }
 
 // Would steps `time` and `time+1` see the same kind of source row (both injected, or both not)?
+// Decided from src_size0 and time alone -- identical on every slab, whether or not it owns a source cell -- so
+// linked slabs (one process per GPU, each deciding for itself) always pair the same steps.
 static bool same_source_regime(const fdtd_b200_plan *p, int time)
 {
-    if (p->ncells_all == 0 && p->ncells2 == 0) return true;
+    if (p->src_size0 <= 0) return true;
     const bool a = time >= 0 && time < p->src_size0, b = time + 1 >= 0 && time + 1 < p->src_size0;
     return a == b;
 }
@@ -792,7 +791,7 @@ int fdtd::plan_prepare(fdtd_b200_plan *p)
     const bool can_tma = tma_supported(p->g);
     int want = p->opt_kernel;
     // auto: the streaming kernel needs enough planes x tiles to hide its per-plane latency chain; below ~110^3
-    // points a step is a few microseconds and the one-point-per-thread kernel wins (profiles/r01_small_grids.txt)
+    // points a step is a few microseconds and the one-point-per-thread kernel wins (profiles/r02_small_grids.txt)
     const long long npts = (long long)(p->g.X1 - p->g.X0) * (p->g.Y1 - p->g.Y0) * (p->g.Z1 - p->g.Z0);
     const bool linked = p->link.peer_u[0] || p->link.peer_u[1];
     if (want == 0) want = (can_tma && (npts >= 1400000 || linked)) ? 2 : 1;

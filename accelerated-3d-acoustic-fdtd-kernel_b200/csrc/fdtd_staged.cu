@@ -240,6 +240,16 @@ extern "C" int fdtd_b200_plan_run_staged(fdtd_b200_plan *p, float *h_u, const fl
     bool jobs_closed = false;
     std::atomic<int> thread_rc{0};
     std::thread t_up, t_down;
+    // a worker thread failed: record the first error and wake whoever waits on cv (the main thread in
+    // upload_through, the unpacking thread waiting for jobs) so the call returns the error instead of hanging
+    auto fail = [&](int code) {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            int expected = 0;
+            thread_rc.compare_exchange_strong(expected, code);
+        }
+        cv.notify_all();
+    };
     auto join_threads = [&] {
         {
             std::lock_guard<std::mutex> lk(mu);
@@ -251,7 +261,7 @@ extern "C" int fdtd_b200_plan_run_staged(fdtd_b200_plan *p, float *h_u, const fl
         if (have_staging) staging_release(), have_staging = false;
     };
     stop_threads = [&] {
-        if (t_up.joinable() || t_down.joinable()) thread_rc.store(thread_rc.load() ? thread_rc.load() : (int)cudaErrorUnknown);
+        if (t_up.joinable() || t_down.joinable()) fail((int)cudaErrorUnknown);
         join_threads();
     };
     cudaEvent_t tl[4] = {nullptr, nullptr, nullptr, nullptr};  // FDTD_B200_TRACE=1: start, H2D end, compute end, D2H end
@@ -287,7 +297,10 @@ extern "C" int fdtd_b200_plan_run_staged(fdtd_b200_plan *p, float *h_u, const fl
                     e = cudaMemcpyAsync(dstp, slot + r * n, n * sizeof(float), cudaMemcpyHostToDevice, s_up);
                 }
                 if (e == cudaSuccess) e = cudaEventRecord(ev_up[c], s_up);
-                if (e != cudaSuccess) thread_rc.store((int)e);
+                if (e != cudaSuccess) {
+                    fail((int)e);
+                    break;
+                }
                 {
                     std::lock_guard<std::mutex> lk(mu);
                     up_ready = c + 1;
@@ -300,11 +313,12 @@ extern "C" int fdtd_b200_plan_run_staged(fdtd_b200_plan *p, float *h_u, const fl
             CopyPool pool(kthreads);
             std::vector<cudaEvent_t> evs;
             DownJob pending{nullptr, 0, 0};
+            cudaEvent_t pending_landed = nullptr;  // the pending job's own "copy has landed" event
             int j = 0, pending_slot = 0;
             auto unpack = [&](const DownJob &d, int slot_i, cudaEvent_t landed) {
-                cudaError_t e = cudaEventSynchronize(landed);
+                cudaError_t e = landed ? cudaEventSynchronize(landed) : cudaErrorUnknown;
                 if (e != cudaSuccess) {
-                    thread_rc.store((int)e);
+                    fail((int)e);
                     return;
                 }
                 const size_t n = (size_t)d.n * plane;
@@ -329,18 +343,19 @@ extern "C" int fdtd_b200_plan_run_staged(fdtd_b200_plan *p, float *h_u, const fl
                     e = cudaMemcpyAsync(slot + r * n, p->d_u + r * lvl + (size_t)d.x0 * plane, n * sizeof(float), cudaMemcpyDeviceToHost, s_down);
                 if (e == cudaSuccess) e = cudaEventCreateWithFlags(&landed, cudaEventDisableTiming);
                 if (e == cudaSuccess) e = cudaEventRecord(landed, s_down);
-                if (e != cudaSuccess) thread_rc.store((int)e);
+                if (e != cudaSuccess) fail((int)e);
                 if (landed) evs.push_back(landed);
-                if (pending.n > 0) unpack(pending, pending_slot, evs[evs.size() - 2]);
+                if (pending.n > 0) unpack(pending, pending_slot, pending_landed);
                 if (e != cudaSuccess) {
                     pending.n = 0;
                     break;
                 }
                 pending = d;
+                pending_landed = landed;
                 pending_slot = slot_i;
                 ++j;
             }
-            if (pending.n > 0 && !evs.empty()) unpack(pending, pending_slot, evs.back());
+            if (pending.n > 0) unpack(pending, pending_slot, pending_landed);
             for (cudaEvent_t e : evs) cudaEventDestroy(e);
         });
     }
@@ -443,7 +458,7 @@ extern "C" int fdtd_b200_plan_run_staged(fdtd_b200_plan *p, float *h_u, const fl
     }
     if (!rc) rc = upload_through((bounce ? nsub : nchunks) - 1);  // trailing halo planes (the device copy stays complete for later runs)
     if (bounce) {
-        if (rc) thread_rc.store(rc);
+        if (rc) fail(rc);
         join_threads();  // all chunks are on their way, all finished planes are back in the caller's array
         if (!rc) rc = thread_rc.load();
     }

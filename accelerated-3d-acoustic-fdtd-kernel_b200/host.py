@@ -49,6 +49,14 @@ class Profiler(C.Structure):  # main.cpp:47-50
     _fields_ = [("section0", C.c_double), ("section1", C.c_double)]
 
 
+class Checksum(C.Structure):  # fdtd_b200_checksum
+    _fields_ = [("bit_sum", C.c_ulonglong), ("pos_sum", C.c_ulonglong), ("nonzero", C.c_ulonglong),
+                ("nonfinite", C.c_ulonglong), ("sum_sq", C.c_double), ("max_abs", C.c_float), ("reserved", C.c_int)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+
+
 class Geometry(C.Structure):  # fdtd_b200_geometry
     _fields_ = [
         ("nx", C.c_int), ("ny", C.c_int), ("nz", C.c_int),
@@ -100,6 +108,8 @@ def lib():
     L.fdtd_b200_plan_level_elems.restype, L.fdtd_b200_plan_level_elems.argtypes = C.c_size_t, [vp]
     L.fdtd_b200_plan_upload.restype, L.fdtd_b200_plan_upload.argtypes = i, [vp, vp, vp]
     L.fdtd_b200_plan_download.restype, L.fdtd_b200_plan_download.argtypes = i, [vp, vp]
+    L.fdtd_b200_plan_download_window.restype, L.fdtd_b200_plan_download_window.argtypes = i, [vp] + [i] * 7 + [vp]
+    L.fdtd_b200_plan_checksum.restype, L.fdtd_b200_plan_checksum.argtypes = i, [vp] + [i] * 7 + [C.POINTER(Checksum)]
     L.fdtd_b200_plan_fill.restype, L.fdtd_b200_plan_fill.argtypes = i, [vp, f, f]
     L.fdtd_b200_plan_fill_dense.restype, L.fdtd_b200_plan_fill_dense.argtypes = i, [vp]
     L.fdtd_b200_plan_set_sources.restype, L.fdtd_b200_plan_set_sources.argtypes = i, [vp, vp, i, i, vp, i, i, i, i]
@@ -136,7 +146,7 @@ def exported_symbols():
     return [
         "Kernel_CUDA_Optimized", "Kernel_B200", "FDTD_SetRuntimeConfig",
         "fdtd_b200_plan_create", "fdtd_b200_plan_destroy", "fdtd_b200_plan_u", "fdtd_b200_plan_m",
-        "fdtd_b200_plan_level", "fdtd_b200_plan_probe_fuse", "fdtd_b200_plan_level_elems", "fdtd_b200_plan_upload", "fdtd_b200_plan_download", "fdtd_b200_plan_fill",
+        "fdtd_b200_plan_level", "fdtd_b200_plan_probe_fuse", "fdtd_b200_plan_level_elems", "fdtd_b200_plan_upload", "fdtd_b200_plan_download", "fdtd_b200_plan_download_window", "fdtd_b200_plan_checksum", "fdtd_b200_plan_fill",
         "fdtd_b200_plan_fill_dense", "fdtd_b200_plan_set_sources", "fdtd_b200_plan_run", "fdtd_b200_plan_run_staged",
         "fdtd_b200_plan_last_launches", "fdtd_b200_plan_last_kernel_seconds", "fdtd_b200_plan_set_option",
         "fdtd_b200_plan_get_option", "fdtd_b200_plan_ipc_export", "fdtd_b200_plan_ipc_attach",
@@ -330,6 +340,34 @@ class Plan:
         out = np.empty(self.shape, np.float32) if out is None else out
         _check(lib().fdtd_b200_plan_download(self._h, out.ctypes.data), "fdtd_b200_plan_download")
         return out
+
+    def _window(self, window):
+        """(x0, x1, y0, y1, z0, z1) in padded local coordinates; None = the whole padded level."""
+        if window is None:
+            return (0, self.shape[1], 0, self.shape[2], 0, self.shape[3])
+        w = tuple(int(v) for v in window)
+        if len(w) != 6:
+            raise ValueError("window = (x0, x1, y0, y1, z0, z1)")
+        return w
+
+    def interior(self):
+        """The window of the cells Section0 updates."""
+        return (HALO, self.shape[1] - HALO, HALO, self.shape[2] - HALO, HALO, self.shape[3] - HALO)
+
+    def download_window(self, ring_level: int, window) -> np.ndarray:
+        """One ring level on [x0,x1) x [y0,y1) x [z0,z1) (padded local coordinates) as a dense array."""
+        w = self._window(window)
+        out = np.empty((w[1] - w[0], w[3] - w[2], w[5] - w[4]), np.float32)
+        _check(lib().fdtd_b200_plan_download_window(self._h, ring_level, *w, out.ctypes.data),
+               "fdtd_b200_plan_download_window")
+        return out
+
+    def checksum(self, ring_level: int, window=None) -> dict:
+        """Device-side checksum of a window: order-independent integer sums (they add up over slabs), max|u|, sum u^2."""
+        c = Checksum()
+        _check(lib().fdtd_b200_plan_checksum(self._h, ring_level, *self._window(window), C.byref(c)),
+               "fdtd_b200_plan_checksum")
+        return c.as_dict()
 
     def fill(self, u_value=0.0, m_value=1.5):
         _check(lib().fdtd_b200_plan_fill(self._h, u_value, m_value), "fdtd_b200_plan_fill")

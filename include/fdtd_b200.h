@@ -107,6 +107,32 @@ size_t fdtd_b200_plan_level_elems(fdtd_b200_plan *plan); /* (nx+8)(ny+8)(nz+8) *
 /* Host <-> device staging of whole arrays (either pointer may be NULL to skip it). */
 int fdtd_b200_plan_upload(fdtd_b200_plan *plan, const float *h_u, const float *h_m);
 int fdtd_b200_plan_download(fdtd_b200_plan *plan, float *h_u);
+/*
+ * A window of one ring level, [x0,x1) x [y0,y1) x [z0,z1) in PADDED LOCAL coordinates (interior starts at 4),
+ * copied to host as a dense float[x1-x0][y1-y0][z1-z0] (SURVEY 8b "_window"): what a harness needs to compare a
+ * 1024^3 / 2048^3 run with the reference on cropped grids around the sources and across slab seams
+ * (main.cpp:573-604 compares all three levels) without pulling 13-104 GB.
+ */
+int fdtd_b200_plan_download_window(fdtd_b200_plan *plan, int ring_level, int x0, int x1, int y0, int y1, int z0,
+                                   int z1, float *host);
+/*
+ * Checksum of a window of one ring level (SURVEY 8b "_checksum"), computed on the device.  bit_sum / pos_sum /
+ * nonzero / nonfinite are integer sums (mod 2^64) and therefore independent of the summation order: the sums of
+ * the slabs' interior windows equal the single-GPU sums.  pos_sum weights every bit pattern with 1 + its GLOBAL
+ * padded linear index ((X + x_offset)*nyp + Y)*nzp + Z, so a misplaced plane changes it.  sum_sq (double) and
+ * max_abs skip non-finite cells.
+ */
+typedef struct {
+    unsigned long long bit_sum;
+    unsigned long long pos_sum;
+    unsigned long long nonzero;   /* cells whose value is not +-0 */
+    unsigned long long nonfinite; /* Inf / NaN cells */
+    double sum_sq;
+    float max_abs;
+    int reserved;
+} fdtd_b200_checksum;
+int fdtd_b200_plan_checksum(fdtd_b200_plan *plan, int ring_level, int x0, int x1, int y0, int y1, int z0, int z1,
+                            fdtd_b200_checksum *out);
 /* Device-side constant fill of all three levels / of m (the driver's synthetic init, main.cpp:351-352). */
 int fdtd_b200_plan_fill(fdtd_b200_plan *plan, float u_value, float m_value);
 /* Dense parity field of main.cpp:525-532 generated on the device from the GLOBAL linear index. */

@@ -168,3 +168,46 @@ def test_one_process_per_gpu_over_ipc(pkg, oracle, tmp_path, world, t_fuse):
     out_path = str(tmp_path / "out.npy")
     mp.spawn(_ipc_worker, args=(world, _free_port(), shape, T, S, out_path, t_fuse), nprocs=world, join=True)
     assert bits_equal(np.load(out_path), ref)
+
+
+@pytest.mark.parametrize("t_fuse", [1, 2])
+def test_linked_slabs_fuse_sources_even_when_fusion_is_off(pkg, oracle, t_fuse):
+    """fuse_inject = 0 asks for the stand-alone scatter, but a linked slab pushes its boundary planes to the neighbour
+    inside the Section0 launch: a source on a boundary plane must already be in them.  Linked slabs therefore always
+    fuse their interior cells; sources sit on and next to the seam."""
+    from oracle import windows as W
+
+    shape, T, S = (64, 32, 64), 11, 8
+    u, m, src, crd = W.dense_seam_case(5, shape, T, S, 2)
+    ref = u.copy()
+    oracle.run(ref, m, src, crd, impl="port")
+    ls = pkg.LocalSlabs(*shape, [0, 0], options={"fuse_inject": 0, "t_fuse": t_fuse})
+    ls.upload(u, m)
+    ls.set_sources(src, crd)
+    ls.run(0, T - 1)
+    out = np.zeros_like(u)
+    ls.download(out)
+    ls.close()
+    assert bits_equal(out, ref)
+
+
+def test_pairing_does_not_depend_on_source_ownership(pkg, oracle):
+    """The src table ends before the run does (src_size0 - 1 < time_M): the step that crosses the end of src must not be
+    paired, on EVERY slab -- including the one that owns no source cell (the decision used to look at slab 0)."""
+    from oracle import windows as W
+
+    shape, T = (96, 32, 64), 16
+    u, m, src, crd = W.dense_seam_case(6, shape, T, 3, 1)
+    crd[:, 0] = np.float32(80 * 0.1) + np.float32(0.03)  # every source in the LAST slab; slab 0 owns none
+    src = src[:10]                                        # src ends at step 9 (odd offset from the timed boundary)
+    ref = u.copy()
+    oracle.run(ref, m, src, crd, impl="port", time_M=T - 1)
+    ls = pkg.LocalSlabs(*shape, [0, 0, 0], options={"t_fuse": 2})
+    ls.upload(u, m)
+    ls.set_sources(src, crd)
+    ls.run(0, T - 1)
+    out = np.zeros_like(u)
+    ls.download(out)
+    assert ls.plans[0].get_option("t_fuse_used") == 2
+    ls.close()
+    assert bits_equal(out, ref)

@@ -271,3 +271,22 @@ def test_512_bench_headline_configuration_within_tolerance(pkg, oracle):
     assert np.abs(a - b).max() <= 1e-5 * np.abs(b).max()
     den = (np.abs(ref) < np.finfo(np.float32).tiny) & (ref != 0)
     assert den.any() and np.count_nonzero(out[den]) > 0.9 * den.sum()
+
+
+@pytest.mark.parametrize("exact", [1, 0])
+@pytest.mark.parametrize("t_fuse", [1, 2])
+def test_dense_256_random_field(pkg, oracle, exact, t_fuse):
+    """BASELINE configs[1] size with a DENSE random field and model (every cell significant, unlike the benchmark's
+    spike), sources included: the TMA kernels in both arithmetic modes, one and two steps per launch.
+    exact: 0 ulp vs the oracle; contracted: relative L2 < 1e-4 AND max-abs <= 1e-5 x peak |u| (north_star)."""
+    shape, T, S = (256, 256, 256), 12, 6
+    u, m, src, crd = fused_case(77, shape, T, S)
+    ref = u.copy()
+    oracle.run(ref, m, src, crd, impl="port", threads=8)
+    out, t, info = run_plan(pkg, u, m, src, crd, options={"exact": exact, "t_fuse": t_fuse})
+    assert info["kernel_used"] == 2 and info["t_fuse_used"] == t_fuse
+    if exact:
+        assert bits_equal(out, ref)
+    else:
+        assert oracle.rel_l2(out, ref) < REL_L2_TOL
+        assert float(np.abs(out - ref).max()) <= 1e-5 * float(np.abs(ref).max())

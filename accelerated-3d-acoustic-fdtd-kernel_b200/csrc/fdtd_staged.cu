@@ -133,6 +133,55 @@ class CopyPool {
     bool stop_ = false;
 };
 
+// The halo shell of planes [xa, xb) of ONE level: every cell outside the box [X0,X1) x [Y0,Y1) x [Z0,Z1).  Planes
+// outside [X0, X1) belong to it whole; of an interior plane only the y-halo rows and, per interior row, the
+// (nzp - Z1) + Z0 floats that straddle the end of one row and the start of the next (contiguous in memory).
+// `each(offset_floats, pitch_floats, width_floats, height)` is called for a handful of (strided) pieces, offsets
+// relative to plane xa.  Pieces may overlap by a few halo floats; none touches a cell of the box.
+template <class F>
+void for_each_shell_piece(const fdtd::Grid &g, int xa, int xb, F &&each)
+{
+    const size_t plane = (size_t)g.nyp * g.nzp;
+    const int lo_end = std::min(xb, std::max(xa, g.X0)), hi_begin = std::max(xa, std::min(xb, g.X1));
+    if (lo_end > xa) each((size_t)0, plane, (size_t)(lo_end - xa) * plane, (size_t)1);                 // x-halo planes below the box
+    if (xb > hi_begin) each((size_t)(hi_begin - xa) * plane, plane, (size_t)(xb - hi_begin) * plane, (size_t)1);  // ... above
+    const int ia = lo_end, ib = hi_begin;  // interior planes of this range
+    if (ib <= ia) return;
+    const size_t base = (size_t)(ia - xa) * plane;
+    // rows [0, Y0) of the first interior plane and the first Z0 floats of its row Y0
+    each(base, plane, (size_t)g.Y0 * g.nzp + g.Z0, (size_t)1);
+    // row seams: from the tail of row Y0 of plane ia to the tail of row Y1-1 of plane ib-1, every row in between
+    const size_t first_row = (size_t)g.Y0, last_row = (size_t)(ib - 1 - ia) * g.nyp + (g.Y1 - 1);
+    each(base + first_row * g.nzp + g.Z1, (size_t)g.nzp, (size_t)(g.nzp - g.Z1 + g.Z0), last_row - first_row + 1);
+    // y-halo bands: rows [Y1, nyp) of plane x and rows [0, Y0) of plane x+1, x = ia .. ib-2
+    if (ib - ia > 1) each(base + (size_t)g.Y1 * g.nzp, plane, (size_t)(g.nyp - g.Y1 + g.Y0) * g.nzp, (size_t)(ib - 1 - ia));
+    // rows [Y1, nyp) of the last interior plane
+    each(base + (size_t)(ib - 1 - ia) * plane + (size_t)g.Y1 * g.nzp, plane, (size_t)(g.nyp - g.Y1) * g.nzp, (size_t)1);
+}
+
+// host -> device copy of the planes [xa, xb) of one level; shell = only the halo shell (the box is write-before-read)
+cudaError_t h2d_level(float *dst, const float *src, const fdtd::Grid &g, int xa, int xb, bool shell, cudaStream_t st)
+{
+    const size_t plane = (size_t)g.nyp * g.nzp;
+    if (!shell) return cudaMemcpyAsync(dst, src, (size_t)(xb - xa) * plane * sizeof(float), cudaMemcpyHostToDevice, st);
+    cudaError_t rc = cudaSuccess;
+    for_each_shell_piece(g, xa, xb, [&](size_t off, size_t pitch, size_t width, size_t height) {
+        if (rc != cudaSuccess) return;
+        rc = height == 1 ? cudaMemcpyAsync(dst + off, src + off, width * sizeof(float), cudaMemcpyHostToDevice, st)
+                         : cudaMemcpy2DAsync(dst + off, pitch * sizeof(float), src + off, pitch * sizeof(float), width * sizeof(float),
+                                             height, cudaMemcpyHostToDevice, st);
+    });
+    return rc;
+}
+
+// the same pieces with memcpy (caller's pageable array -> pinned slot, both addressed from plane xa)
+void pack_shell(float *dst, const float *src, const fdtd::Grid &g, int xa, int xb)
+{
+    for_each_shell_piece(g, xa, xb, [&](size_t off, size_t pitch, size_t width, size_t height) {
+        for (size_t r = 0; r < height; ++r) memcpy(dst + off + r * pitch, src + off + r * pitch, width * sizeof(float));
+    });
+}
+
 bool is_pinned(const void *q)
 {
     cudaPointerAttributes at{};
@@ -172,6 +221,10 @@ extern "C" int fdtd_b200_plan_run_staged(fdtd_b200_plan *p, float *h_u, const fl
         const long long npts = (long long)nx * (p->g.Y1 - p->g.Y0) * (p->g.Z1 - p->g.Z0);
         if (npts < 8000000 || T < 1) return (int)cudaErrorNotSupported;
         B = (int)(((long long)(nx + 2 * T) * T / 1600 + 7) / 8 * 8);
+        // ... and a launch should carry ~2M points: below that its fixed cost (launch, pipeline prologue) dominates and
+        // the skewed loop becomes the bottleneck instead of the wire (256^3: 32 planes per block instead of 16)
+        const long long per_plane = (long long)(p->g.Y1 - p->g.Y0) * (p->g.Z1 - p->g.Z0);
+        B = std::max(B, (int)((2000000 / per_plane + 7) / 8 * 8));
         B = std::max(16, std::min(B, nx / 2));
     }
     if (B < 8 || linked || T < 1 || nx < 2 * B || (src_active && (p->ncells_halo > 0 || !p->opt_fuse))) return (int)cudaErrorNotSupported;
@@ -194,6 +247,9 @@ extern "C" int fdtd_b200_plan_run_staged(fdtd_b200_plan *p, float *h_u, const fl
 
     const Grid g = p->g;
     const size_t plane = (size_t)g.nyp * g.nzp, lvl = (size_t)g.lvl;
+    // Level t2 of the first step is written over its whole box before anything reads it (every step covers
+    // [X0, X1) x [Y0, Y1) x [Z0, Z1)), so only its halo shell has to travel: a quarter of the upload less.
+    const int shell_level = env_int("FDTD_B200_SHELL_UPLOAD", 1) ? (((time_m + 1) % 3) + 3) % 3 : -1;
     cudaStream_t s_up = nullptr, s_down = nullptr;
     std::vector<cudaEvent_t> ev_up, ev_done, ev_t;
     std::function<void()> stop_threads = [] {};
@@ -290,11 +346,15 @@ extern "C" int fdtd_b200_plan_run_staged(fdtd_b200_plan *p, float *h_u, const fl
                 const size_t x0 = (size_t)c * Bb, n = std::min<size_t>(Bb, g.nxp - x0) * plane;
                 float *slot = static_cast<float *>(g_staging.up[c % 3]);
                 cudaError_t e = c >= 3 ? cudaEventSynchronize(ev_up[c - 3]) : cudaSuccess;  // the slot's previous sub-chunk has left
+                const int xa = (int)x0, xb = (int)(x0 + n / plane);
                 for (int r = 0; r < 4 && e == cudaSuccess; ++r) {
                     const float *srcp = r < 3 ? h_u + r * lvl + x0 * plane : h_m + x0 * plane;
                     float *dstp = r < 3 ? p->d_u + r * lvl + x0 * plane : p->d_m + x0 * plane;
-                    pool.copy(slot + r * n, srcp, n * sizeof(float));
-                    e = cudaMemcpyAsync(dstp, slot + r * n, n * sizeof(float), cudaMemcpyHostToDevice, s_up);
+                    if (r == shell_level)
+                        pack_shell(slot + r * n, srcp, g, xa, xb);
+                    else
+                        pool.copy(slot + r * n, srcp, n * sizeof(float));
+                    e = h2d_level(dstp, slot + r * n, g, xa, xb, r == shell_level, s_up);
                 }
                 if (e == cudaSuccess) e = cudaEventRecord(ev_up[c], s_up);
                 if (e != cudaSuccess) {
@@ -369,9 +429,9 @@ extern "C" int fdtd_b200_plan_run_staged(fdtd_b200_plan *p, float *h_u, const fl
         }
         for (; uploaded <= c_last && uploaded < nchunks; ++uploaded) {
             const size_t x0 = (size_t)uploaded * B, n = std::min<size_t>(B, g.nxp - x0) * plane;
+            const int xa = (int)x0, xb = (int)(x0 + n / plane);
             for (int r = 0; r < 3; ++r)
-                FDTD_CHECK(cudaMemcpyAsync(p->d_u + r * lvl + x0 * plane, h_u + r * lvl + x0 * plane, n * sizeof(float),
-                                           cudaMemcpyHostToDevice, s_up));
+                FDTD_CHECK(h2d_level(p->d_u + r * lvl + x0 * plane, h_u + r * lvl + x0 * plane, g, xa, xb, r == shell_level, s_up));
             FDTD_CHECK(cudaMemcpyAsync(p->d_m + x0 * plane, h_m + x0 * plane, n * sizeof(float), cudaMemcpyHostToDevice, s_up));
             FDTD_CHECK(cudaEventCreateWithFlags(&ev_up[uploaded], cudaEventDisableTiming));
             FDTD_CHECK(cudaEventRecord(ev_up[uploaded], s_up));

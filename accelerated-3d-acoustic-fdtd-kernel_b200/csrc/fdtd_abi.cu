@@ -39,6 +39,15 @@ static int kernel_entry(struct dataobj *m_vec, struct dataobj *src_vec, struct d
     s.gx_m = x_m;
     s.gx_M = x_M;
     s.deviceid = deviceid;
+    // Space order: the driver is compiled with STENCIL_ORDER and pads every axis with HALO == order cells
+    // (main.cpp:27-32,331-334) but does not pass the order.  FDTD_B200_STENCIL_ORDER names it; otherwise it is read off
+    // the padding when the call covers the whole interior from 0 (what the driver does); anything else means order 4.
+    s.space_order = env_int("FDTD_B200_STENCIL_ORDER", 0);
+    if (s.space_order == 0) {
+        s.space_order = 4;
+        const int px = s.nxp - (x_M - x_m + 1), py = s.nyp - (y_M - y_m + 1), pz = s.nzp - (z_M - z_m + 1);
+        if (x_m == 0 && y_m == 0 && z_m == 0 && px == py && py == pz && px % 4 == 0 && px >= 12 && px <= 24) s.space_order = px / 2;
+    }
 
     // FDTD_B200_TRACE=1 prints the host-side phases of the call (staging dominates at large grids)
     const char *tr = getenv("FDTD_B200_TRACE");

@@ -26,6 +26,16 @@ struct Coef {
     float fx1, fx2, fy1, fy2, fz1, fz2, f0;
 };
 
+// Space orders beyond the reference's 4 (main.cpp is parameterised by STENCIL_ORDER, HALO == order):
+// second-derivative weights c[0..R] of order 2R (R = order/2 <= 6) and their contracted-form products.
+#define FDTD_MAX_RADIUS 6
+struct OrderCoef {
+    int R;
+    float c[FDTD_MAX_RADIUS + 1];                                                  // exact form: c[0] centre, c[k] = +-k
+    float fx[FDTD_MAX_RADIUS + 1], fy[FDTD_MAX_RADIUS + 1], fz[FDTD_MAX_RADIUS + 1];  // dt2*r{2,3,4}*c[k]
+    float f0;                                                                      // dt2*(r2+r3+r4)*c[0]
+};
+
 // One grid cell that receives source contributions (padded local coordinates).
 struct SourceCell {
     int X, Y, Z;

@@ -18,6 +18,20 @@ struct StepArgs {
 // --- generic kernel: any extents / alignment, one point per thread, loads through L1/L2.
 int launch_stencil_generic(const StepArgs &a, bool exact, cudaStream_t stream);
 
+// --- the same for space orders 6..12 (radius 3..6, halo = order cells): exact mode follows the oracle's generalisation
+// of openacc.cpp:102-107 (outermost neighbour pair first), contracted mode the FMA form.
+int launch_stencil_order(const StepArgs &a, const OrderCoef &oc, bool exact, cudaStream_t stream);
+// Receiver sampling: rec_row[p] = sum over the in-range trilinear corners of ((wx*wy)*wz)*u[corner],
+// x outermost / z innermost; pos/frac are precomputed on the host in IEEE fp32 (same arithmetic as the injection).
+struct ReceiverPoint {
+    int X, Y, Z;          // padded local base corner
+    float fx, fy, fz;     // fractions
+    unsigned mask;        // bit rx*4+ry*2+rz set = corner in range (openacc.cpp:132 bounds) and owned data
+    int index;            // column of rec[time][index]
+};
+int launch_sample_receivers(const float *u_level, const Grid &g, const ReceiverPoint *pts, int npts, float *rec_row,
+                            cudaStream_t stream);
+
 // --- 2.5D x-streaming kernel: TMA -> mbarrier ring in shared memory -> register queue along x.
 struct TmaConfig {
     int ty = 0, tz = 0;  // (y,z) tile; 0 = auto

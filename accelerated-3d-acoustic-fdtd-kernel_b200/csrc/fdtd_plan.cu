@@ -22,7 +22,7 @@
 
 using namespace fdtd;
 
-static void shape_from_geometry(const fdtd_b200_geometry *geo, PlanShape &s);
+static void shape_from_geometry(const fdtd_b200_geometry *geo, PlanShape &s, int space_order = 4);
 static void grid_from_shape(const PlanShape &s, Grid &g);
 
 // ---------------------------------------------------------------------------- runtime config
@@ -163,10 +163,12 @@ int fdtd::plan_create_internal(const PlanShape &s, fdtd_b200_plan **out, bool ca
 {
     if (!out) return (int)cudaErrorInvalidValue;
     *out = nullptr;
-    // extents must be non-empty (cuda_optimized.cu:347) and leave the radius-2 star inside the arrays
+    // extents must be non-empty (cuda_optimized.cu:347) and leave the radius-R star inside the arrays
     if (s.x_M < s.x_m || s.y_M < s.y_m || s.z_M < s.z_m) return (int)cudaErrorInvalidValue;
-    if (s.x_m + FDTD_HALO - 2 < 0 || s.y_m + FDTD_HALO - 2 < 0 || s.z_m + FDTD_HALO - 2 < 0 ||
-        s.x_M + FDTD_HALO + 2 >= s.nxp || s.y_M + FDTD_HALO + 2 >= s.nyp || s.z_M + FDTD_HALO + 2 >= s.nzp)
+    if (s.space_order < 4 || s.space_order > 2 * FDTD_MAX_RADIUS || (s.space_order & 1)) return (int)cudaErrorInvalidValue;
+    const int H = s.space_order, R = s.space_order / 2;
+    if (s.x_m + H - R < 0 || s.y_m + H - R < 0 || s.z_m + H - R < 0 || s.x_M + H + R >= s.nxp || s.y_M + H + R >= s.nyp ||
+        s.z_M + H + R >= s.nzp)
         return (int)cudaErrorInvalidValue;
     if (s.deviceid != -1) FDTD_CHECK(cudaSetDevice(s.deviceid));
 
@@ -189,6 +191,22 @@ int fdtd::plan_create_internal(const PlanShape &s, fdtd_b200_plan **out, bool ca
     p->k.fz1 = p->k.dt2 * p->k.r4 * 1.333333330F;
     p->k.fz2 = p->k.dt2 * p->k.r4 * -8.33333333e-2F;
     p->k.f0 = p->k.dt2 * (p->k.r2 + p->k.r3 + p->k.r4) * -2.50F;
+    {   // weights of space order 2R: the correctly rounded floats of the exact rationals (order 4 = the reference's literals)
+        static const float tab[5][FDTD_MAX_RADIUS + 1] = {
+            {-2.5F, 1.33333337F, -0.0833333358F},
+            {-2.72222233F, 1.5F, -0.150000006F, 0.0111111114F},
+            {-2.84722233F, 1.60000002F, -0.200000003F, 0.0253968257F, -0.0017857143F},
+            {-2.92722225F, 1.66666663F, -0.238095239F, 0.039682541F, -0.00496031763F, 0.000317460304F},
+            {-2.98277783F, 1.71428573F, -0.267857134F, 0.0529100522F, -0.00892857183F, 0.001038961F, -6.01250613e-05F}};
+        p->oc.R = R;
+        for (int k = 0; k <= R; ++k) {
+            p->oc.c[k] = tab[R - 2][k];
+            p->oc.fx[k] = p->k.dt2 * p->k.r2 * tab[R - 2][k];
+            p->oc.fy[k] = p->k.dt2 * p->k.r3 * tab[R - 2][k];
+            p->oc.fz[k] = p->k.dt2 * p->k.r4 * tab[R - 2][k];
+        }
+        p->oc.f0 = p->k.dt2 * (p->k.r2 + p->k.r3 + p->k.r4) * tab[R - 2][0];
+    }
 
     p->opt_kernel = env_int("FDTD_B200_KERNEL", 0);
     p->opt_exact = env_int("FDTD_B200_EXACT", 1);
@@ -236,10 +254,23 @@ extern "C" int fdtd_b200_plan_create(const fdtd_b200_geometry *geo, fdtd_b200_pl
     return plan_create_internal(s, out);
 }
 
+extern "C" int fdtd_b200_plan_create_order(const fdtd_b200_geometry *geo, int space_order, fdtd_b200_plan **out)
+{
+    if (!geo || geo->nx < 1 || geo->ny < 1 || geo->nz < 1) return (int)cudaErrorInvalidValue;
+    if (space_order < 4 || space_order > 2 * FDTD_MAX_RADIUS || (space_order & 1)) return (int)cudaErrorInvalidValue;
+    PlanShape s;
+    shape_from_geometry(geo, s, space_order);
+    if (s.x_offset < 0 || s.x_offset + geo->nx - 1 > s.gx_M) return (int)cudaErrorInvalidValue;
+    if (space_order != 4 && (s.x_offset != 0 || s.gx_M != geo->nx - 1)) return (int)cudaErrorNotSupported;  // x-slabs: order 4 only
+    return plan_create_internal(s, out);
+}
+
 extern "C" int fdtd_b200_plan_destroy(fdtd_b200_plan *p)
 {
     if (!p) return 0;
     cudaSetDevice(p->dev);
+    cudaFree(p->d_rec_pts);
+    cudaFree(p->d_rec);
     const bool trace = env_int("FDTD_B200_TRACE", 0) > 1;
     const auto t_a = std::chrono::steady_clock::now();
     plan_free_sources(p);
@@ -367,8 +398,8 @@ static void build_source_table(const PlanShape &s, const Grid &g, const float *c
                 for (int rz = 0; rz <= 1; ++rz) {
                     const int i = rx * 4 + ry * 2 + rz;
                     if (!in_range[i]) continue;
-                    const int X = rx + pos[0] - s.x_offset + FDTD_HALO;  // local padded plane
-                    const int Y = ry + pos[1] + FDTD_HALO, Z = rz + pos[2] + FDTD_HALO;
+                    const int X = rx + pos[0] - s.x_offset + s.space_order;  // local padded plane
+                    const int Y = ry + pos[1] + s.space_order, Z = rz + pos[2] + s.space_order;
                     const int gx = rx + pos[0];  // global unpadded x of this corner
                     if (gx < s.gx_m || gx > s.gx_M || Y < g.Y0 || Y >= g.Y1 || Z < g.Z0 || Z >= g.Z1) t.halo_global = true;
                     // ownership along the slab axis: interior planes, plus the physical halo plane at a global end
@@ -384,8 +415,8 @@ static void build_source_table(const PlanShape &s, const Grid &g, const float *c
                     any = true;
                 }
         if (any)
-            t.base_idx[ps] = ((long long)(pos[0] - s.x_offset + FDTD_HALO) * g.nyp + (pos[1] + FDTD_HALO)) * g.nzp +
-                             (pos[2] + FDTD_HALO);
+            t.base_idx[ps] = ((long long)(pos[0] - s.x_offset + s.space_order) * g.nyp + (pos[1] + s.space_order)) * g.nzp +
+                             (pos[2] + s.space_order);
     }
     std::vector<SourceCell> cint, chalo;
     for (auto &kv : cells) {
@@ -422,12 +453,13 @@ static void build_source_table(const PlanShape &s, const Grid &g, const float *c
     for (int x = 0; x < g.nxp; ++x) t.plane_off2[x + 1] += t.plane_off2[x];
 }
 
-static void shape_from_geometry(const fdtd_b200_geometry *geo, PlanShape &s)
+static void shape_from_geometry(const fdtd_b200_geometry *geo, PlanShape &s, int space_order)
 {
     s = PlanShape{};
-    s.nxp = geo->nx + 2 * FDTD_HALO;
-    s.nyp = geo->ny + 2 * FDTD_HALO;
-    s.nzp = geo->nz + 2 * FDTD_HALO;
+    s.space_order = space_order;
+    s.nxp = geo->nx + 2 * space_order;
+    s.nyp = geo->ny + 2 * space_order;
+    s.nzp = geo->nz + 2 * space_order;
     s.x_m = 0;
     s.x_M = geo->nx - 1;
     s.y_m = 0;
@@ -452,12 +484,12 @@ static void grid_from_shape(const PlanShape &s, Grid &g)
     g.nxp = s.nxp;
     g.nyp = s.nyp;
     g.nzp = s.nzp;
-    g.X0 = s.x_m + FDTD_HALO;
-    g.X1 = s.x_M + FDTD_HALO + 1;
-    g.Y0 = s.y_m + FDTD_HALO;
-    g.Y1 = s.y_M + FDTD_HALO + 1;
-    g.Z0 = s.z_m + FDTD_HALO;
-    g.Z1 = s.z_M + FDTD_HALO + 1;
+    g.X0 = s.x_m + s.space_order;
+    g.X1 = s.x_M + s.space_order + 1;
+    g.Y0 = s.y_m + s.space_order;
+    g.Y1 = s.y_M + s.space_order + 1;
+    g.Z0 = s.z_m + s.space_order;
+    g.Z1 = s.z_M + s.space_order + 1;
     g.lvl = (long long)s.nxp * s.nyp * s.nzp;
 }
 
@@ -575,6 +607,94 @@ extern "C" int fdtd_b200_plan_set_sources(fdtd_b200_plan *p, const float *src, i
     return 0;
 }
 
+// ---------------------------------------------------------------------------- receivers
+// rec[time][p] = trilinear sample of the CURRENT level u[t0] at step `time` (the "Section2" of the generated operator
+// this path comes from).  Positions and fractions in IEEE fp32 on the host, exactly as the injection's
+// (openacc.cpp:125-131); a corner outside [m-1, M+1] is skipped.  With x-slabs a receiver belongs to the slab whose
+// planes hold its base corner (the +1 corner then lies at most in the first ghost plane, which holds the neighbour's
+// current values); the two global end slabs also take base corners in the physical halo.
+extern "C" int fdtd_b200_plan_set_receivers(fdtd_b200_plan *p, const float *coords, int nrec, int cstride)
+{
+    if (!p || nrec < 0 || (nrec > 0 && (!coords || cstride < 3))) return (int)cudaErrorInvalidValue;
+    FDTD_CHECK(cudaSetDevice(p->dev));
+    cudaFree(p->d_rec_pts);
+    p->d_rec_pts = nullptr;
+    p->nrec_total = nrec;
+    p->nrec_owned = 0;
+    p->rec_owned.assign((size_t)nrec, 0);
+    p->rec_rows = 0;
+    if (nrec == 0) return 0;
+    const PlanShape &s = p->shape;
+    const Grid &g = p->g;
+    const bool first_slab = s.x_offset + s.x_m == s.gx_m, last_slab = s.x_offset + s.x_M == s.gx_M;
+    const int lo[3] = {s.gx_m, s.y_m, s.z_m}, hi[3] = {s.gx_M, s.y_M, s.z_M};
+    const float o[3] = {s.o_x, s.o_y, s.o_z}, h[3] = {s.h_x, s.h_y, s.h_z};
+    std::vector<ReceiverPoint> pts;
+    for (int r = 0; r < nrec; ++r) {
+        int pos[3], in_range[8];
+        float frac[3], w[8];
+        fdtd_b200_source_table(coords + (size_t)r * cstride, o, h, lo, hi, pos, frac, w, in_range);
+        unsigned mask = 0;
+        for (int i = 0; i < 8; ++i) mask |= in_range[i] ? 1u << i : 0u;
+        const int X = pos[0] - s.x_offset + s.space_order;  // local padded plane of the base corner
+        const bool owned = (X >= g.X0 && X < g.X1) || (first_slab && X < g.X0) || (last_slab && X >= g.X1);
+        if (!owned) continue;
+        p->rec_owned[r] = 1;
+        if (!mask) continue;  // nothing in range: the trace stays 0 (d_rec is zero-filled)
+        pts.push_back(ReceiverPoint{X, pos[1] + s.space_order, pos[2] + s.space_order, frac[0], frac[1], frac[2], mask, r});
+    }
+    p->nrec_owned = (int)pts.size();
+    if (!pts.empty()) {
+        FDTD_CHECK(cudaMalloc(&p->d_rec_pts, pts.size() * sizeof(ReceiverPoint)));
+        FDTD_CHECK(cudaMemcpy(p->d_rec_pts, pts.data(), pts.size() * sizeof(ReceiverPoint), cudaMemcpyHostToDevice));
+    }
+    return 0;
+}
+
+// Traces of the last run: host [rows][nrec_total] (rows = its time steps), owned[nrec_total] = 1 where this slab sampled.
+extern "C" int fdtd_b200_plan_download_receivers(fdtd_b200_plan *p, float *host, int *owned, int *rows)
+{
+    if (!p) return (int)cudaErrorInvalidValue;
+    if (rows) *rows = p->rec_rows;
+    if (owned)
+        for (int r = 0; r < p->nrec_total; ++r) owned[r] = p->rec_owned[r];
+    if (host && p->rec_rows > 0 && p->nrec_total > 0) {
+        FDTD_CHECK(cudaSetDevice(p->dev));
+        FDTD_CHECK(cudaMemcpy(host, p->d_rec, (size_t)p->rec_rows * p->nrec_total * sizeof(float), cudaMemcpyDeviceToHost));
+    }
+    return 0;
+}
+
+// room for (and zeros in) the traces of a run of `rows` steps
+static int plan_prepare_receivers(fdtd_b200_plan *p, int time_m, int rows)
+{
+    p->rec_rows = 0;
+    if (p->nrec_total <= 0) return 0;
+    FDTD_CHECK(cudaSetDevice(p->dev));
+    if (rows > p->rec_rows_cap) {
+        cudaFree(p->d_rec);
+        p->d_rec = nullptr;
+        p->rec_rows_cap = 0;
+        FDTD_CHECK(cudaMalloc(&p->d_rec, (size_t)rows * p->nrec_total * sizeof(float)));
+        p->rec_rows_cap = rows;
+    }
+    FDTD_CHECK(cudaMemsetAsync(p->d_rec, 0, (size_t)rows * p->nrec_total * sizeof(float), p->stream));
+    p->rec_rows = rows;
+    p->rec_time_m = time_m;
+    return 0;
+}
+
+// sample u^{time} (ring level time % 3, wherever it lives) into row time - time_m
+static int plan_sample(fdtd_b200_plan *p, int time)
+{
+    if (p->nrec_owned <= 0) return 0;
+    const int t0 = ((time % 3) + 3) % 3;
+    int rc = launch_sample_receivers(p->d_u + (size_t)p->phys[t0] * p->g.lvl, p->g, p->d_rec_pts, p->nrec_owned,
+                                     p->d_rec + (size_t)(time - p->rec_time_m) * p->nrec_total, p->stream);
+    if (!rc) p->last_launches++;
+    return rc;
+}
+
 // ---------------------------------------------------------------------------- options
 static int *option_slot(fdtd_b200_plan *p, const char *key)
 {
@@ -616,6 +736,8 @@ extern "C" int fdtd_b200_plan_get_option(fdtd_b200_plan *p, const char *key, int
     if (!strcmp(key, "xchunk_used")) { *value = two ? p->tb2.xchunk : (p->tma.valid ? p->tma.xchunk : 0); return 0; }
     if (!strcmp(key, "ncells_fused")) { *value = p->ncells_int; return 0; }
     if (!strcmp(key, "ncells_halo")) { *value = p->ncells_halo; return 0; }
+    if (!strcmp(key, "space_order")) { *value = p->shape.space_order; return 0; }
+    if (!strcmp(key, "nrec_owned")) { *value = p->nrec_owned; return 0; }
     int *slot = option_slot(p, key);
     if (!slot) return (int)cudaErrorInvalidValue;
     *value = *slot;
@@ -660,6 +782,8 @@ static int plan_step(fdtd_b200_plan *p, int time, bool first_of_run, Mark &&mark
     int rc;
     if (p->kernel_used == 2)
         rc = launch_stencil_tma(p->tma, a, p->opt_exact != 0, p->stream);
+    else if (p->kernel_used == 3)
+        rc = launch_stencil_order(a, p->oc, p->opt_exact != 0, p->stream);
     else
         rc = launch_stencil_generic(a, p->opt_exact != 0, p->stream);
     if (rc) return rc;
@@ -731,8 +855,11 @@ static bool same_source_regime(const fdtd_b200_plan *p, int time)
 static int plan_fuse_feasible(fdtd_b200_plan *p, int *out)
 {
     *out = 1;
-    if (p->opt_t_fuse < 2 || p->opt_kernel == 1 || !tma_supported(p->g)) return 0;
+    if (p->opt_t_fuse < 2 || p->opt_kernel == 1 || p->shape.space_order != 4 || !tma_supported(p->g)) return 0;
     const bool linked = p->link.peer_u[0] || p->link.peer_u[1];
+    // receivers on linked slabs read a ghost plane of u^{n+1} that the neighbour's SAME pass writes: one-step passes
+    // (nrec_total is the same on every slab, so all slabs decide alike)
+    if (linked && p->nrec_total > 0) return 0;
     const int nx = p->g.X1 - p->g.X0;
     const long long npts = (long long)nx * (p->g.Y1 - p->g.Y0) * (p->g.Z1 - p->g.Z0);
     if (p->opt_kernel == 0 && npts < 1400000 && !linked) return 0;  // small grids run the generic kernel
@@ -788,8 +915,19 @@ int fdtd::plan_prepare(fdtd_b200_plan *p)
     FDTD_CHECK(cudaSetDevice(p->dev));
     p->last_launches = 0;
     p->last_kernel_seconds = 0.0;
-    const bool can_tma = tma_supported(p->g);
+    const bool can_tma = p->shape.space_order == 4 && tma_supported(p->g);
     int want = p->opt_kernel;
+    if (p->shape.space_order != 4) {  // orders 6..12: the one-point-per-thread kernel with R neighbour pairs per axis
+        if (p->link.peer_u[0] || p->link.peer_u[1]) return (int)cudaErrorNotSupported;
+        p->kernel_used = 3;
+        p->t_fuse_used = 1;
+        if (p->ncells_all > 0 || p->ncells2 > 0) {
+            int rc = launch_gather_mbase(p->d_m, p->d_base_idx, p->d_mbase, p->n_mbase, p->stream);
+            if (rc) return rc;
+            p->last_launches++;
+        }
+        return 0;
+    }
     // auto: the streaming kernel needs enough planes x tiles to hide its per-plane latency chain; below ~110^3
     // points a step is a few microseconds and the one-point-per-thread kernel wins (profiles/r02_small_grids.txt)
     const long long npts = (long long)(p->g.X1 - p->g.X0) * (p->g.Y1 - p->g.Y0) * (p->g.Z1 - p->g.Z0);
@@ -847,6 +985,7 @@ static int run_many(fdtd_b200_plan **ps, int n, int time_m, int time_M, struct p
     }
     for (int i = 0; i < n; ++i) {
         int rc = plan_prepare(ps[i]);
+        if (!rc) rc = plan_prepare_receivers(ps[i], time_m, time_M - time_m + 1);
         if (rc) return rc;
     }
     bool fuse2 = true;
@@ -874,6 +1013,13 @@ static int run_many(fdtd_b200_plan **ps, int n, int time_m, int time_M, struct p
                 });
             } else {
                 rc = plan_step(p, time, time == time_m, [](bool) {});
+            }
+            if (!rc && p->nrec_owned > 0) {  // "Section2": the levels u^{time} (and u^{time+1} of a pass) are final now
+                const bool timed = time >= first_timed;
+                if (timed) r.s1_spans.push_back({r.stamp(p->stream), nullptr});
+                rc = plan_sample(p, time);
+                if (!rc && two) rc = plan_sample(p, time + 1);
+                if (timed) r.s1_spans.back().second = r.stamp(p->stream);
             }
         }
         if (!rc && g_debug_sync) {  // FDTD_B200_SYNC=1: find the launch that faults

@@ -15,6 +15,7 @@ struct PlanShape {
     int x_offset;      // global index of local x = 0
     int gx_m, gx_M;    // GLOBAL x extents (== x_m, x_M for one slab)
     int deviceid;
+    int space_order = 4;  // 4 (the reference's kernels) .. 12; halo cells per side == space_order (main.cpp:27-32)
 };
 
 // cache_buffers: take the field buffers from / return them to the per-process device-buffer cache (used by
@@ -59,6 +60,14 @@ struct fdtd_b200_plan {
     int ncells2 = 0;
     bool src_halo_global = false;
     std::vector<long long> h_base_idx;  // host copy of d_base_idx (the staged run gathers mbase from the host's m)
+
+    // space orders 6..12 (generic kernel only) and receivers
+    fdtd::OrderCoef oc{};
+    fdtd::ReceiverPoint *d_rec_pts = nullptr;
+    int nrec_total = 0, nrec_owned = 0;
+    std::vector<int> rec_owned;        // [nrec_total] 1 = this slab samples the receiver
+    float *d_rec = nullptr;            // [rec_rows_cap][nrec_total]
+    int rec_rows_cap = 0, rec_rows = 0, rec_time_m = 0;
 
     // options
     int opt_kernel = 0, opt_exact = 1, opt_fuse = 1, opt_t_fuse = 1;

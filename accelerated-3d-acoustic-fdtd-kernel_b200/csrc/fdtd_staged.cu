@@ -227,6 +227,7 @@ extern "C" int fdtd_b200_plan_run_staged(fdtd_b200_plan *p, float *h_u, const fl
         B = std::max(B, (int)((2000000 / per_plane + 7) / 8 * 8));
         B = std::max(16, std::min(B, nx / 2));
     }
+    if (p->shape.space_order != 4 || p->nrec_total > 0) return (int)cudaErrorNotSupported;
     if (B < 8 || linked || T < 1 || nx < 2 * B || (src_active && (p->ncells_halo > 0 || !p->opt_fuse))) return (int)cudaErrorNotSupported;
     FDTD_CHECK(cudaSetDevice(p->dev));
     if (timers) timers->section0 = timers->section1 = 0.0;

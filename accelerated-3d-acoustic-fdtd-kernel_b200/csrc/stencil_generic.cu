@@ -55,6 +55,118 @@ int launch_stencil_generic(const StepArgs &a, bool exact, cudaStream_t stream)
     return (int)cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------- space orders 6..12
+// One point per thread like the kernel above; R pairs of neighbours per axis.  EXACT replays the oracle's operation
+// order: the outermost neighbour pair first, which at R = 2 is the reference's (openacc.cpp:102-107).
+template <int R, bool EXACT>
+__global__ void __launch_bounds__(256) stencil_order_kernel(StepArgs a, OrderCoef oc)
+{
+    const int Z = a.g.Z0 + blockIdx.x * blockDim.x + threadIdx.x;
+    const int Y = a.g.Y0 + blockIdx.y * blockDim.y + threadIdx.y;
+    const int X = a.g.X0 + blockIdx.z;
+    if (Z >= a.g.Z1 || Y >= a.g.Y1) return;
+    const long long sy = a.g.nzp, sx = (long long)a.g.nyp * a.g.nzp;
+    const long long c = (long long)X * sx + (long long)Y * sy + Z;
+    const float *__restrict__ u0 = a.u + a.t0 * a.g.lvl;
+    const float *__restrict__ u1 = a.u + a.t1 * a.g.lvl;
+    float *__restrict__ u2 = a.u + a.t2 * a.g.lvl;
+    const float uc = __ldg(u0 + c), up = __ldg(u1 + c), mm = __ldg(a.m + c);
+    float v;
+    if (EXACT) {
+        const float r5 = __fmul_rn(oc.c[0], uc);
+        float dx = r5, dy = r5, dz = r5;
+#pragma unroll
+        for (int k = R; k >= 1; --k) {
+            dx = __fadd_rn(dx, __fmul_rn(oc.c[k], __fadd_rn(__ldg(u0 + c - k * sx), __ldg(u0 + c + k * sx))));
+            dy = __fadd_rn(dy, __fmul_rn(oc.c[k], __fadd_rn(__ldg(u0 + c - k * sy), __ldg(u0 + c + k * sy))));
+            dz = __fadd_rn(dz, __fmul_rn(oc.c[k], __fadd_rn(__ldg(u0 + c - k), __ldg(u0 + c + k))));
+        }
+        v = leapfrog_exact(uc, dx, dy, dz, up, mm, a.k);
+    } else {
+        float acc = oc.f0 * uc;
+#pragma unroll
+        for (int k = R; k >= 1; --k) acc = fmaf(oc.fx[k], __ldg(u0 + c - k * sx) + __ldg(u0 + c + k * sx), acc);
+#pragma unroll
+        for (int k = R; k >= 1; --k) acc = fmaf(oc.fy[k], __ldg(u0 + c - k * sy) + __ldg(u0 + c + k * sy), acc);
+#pragma unroll
+        for (int k = R; k >= 1; --k) acc = fmaf(oc.fz[k], __ldg(u0 + c - k) + __ldg(u0 + c + k), acc);
+        float rm;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rm) : "f"(mm));
+        v = fmaf(acc, rm, fmaf(2.0f, uc, -up));
+    }
+    if (a.sv.ncells > 0) {
+        const int c0 = a.sv.plane_off[X], c1 = a.sv.plane_off[X + 1];
+        for (int i = c0; i < c1; ++i) {
+            const SourceCell cell = a.sv.cells[i];
+            if (cell.Y == Y && cell.Z == Z) v = apply_cell(v, cell, a.sv);
+        }
+    }
+    u2[c] = v;
+}
+
+int launch_stencil_order(const StepArgs &a, const OrderCoef &oc, bool exact, cudaStream_t stream)
+{
+    const int nz = a.g.Z1 - a.g.Z0, ny = a.g.Y1 - a.g.Y0, nx = a.g.X1 - a.g.X0;
+    if (nx <= 0 || ny <= 0 || nz <= 0) return 0;
+    dim3 block(64, 4, 1);
+    if (nz <= 32) block = dim3(32, 8, 1);
+    dim3 grid((nz + block.x - 1) / block.x, (ny + block.y - 1) / block.y, nx);
+    if (grid.y > 65535 || grid.z > 65535) return (int)cudaErrorInvalidValue;
+#define FDTD_ORDER_CASE(R_)                                                          \
+    case R_:                                                                         \
+        if (exact)                                                                   \
+            stencil_order_kernel<R_, true><<<grid, block, 0, stream>>>(a, oc);       \
+        else                                                                         \
+            stencil_order_kernel<R_, false><<<grid, block, 0, stream>>>(a, oc);      \
+        break;
+    switch (oc.R) {
+        FDTD_ORDER_CASE(2)
+        FDTD_ORDER_CASE(3)
+        FDTD_ORDER_CASE(4)
+        FDTD_ORDER_CASE(5)
+        FDTD_ORDER_CASE(6)
+    default:
+        return (int)cudaErrorInvalidValue;
+    }
+#undef FDTD_ORDER_CASE
+    return (int)cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------- receiver sampling
+// One thread per receiver; the eight corners are summed in the oracle's order (x outermost, z innermost), every
+// weight product as ((wx*wy)*wz)*u with one rounding per operation, so the trace is bit-identical to the oracle's.
+__global__ void sample_receivers_kernel(const float *__restrict__ u, Grid g, const ReceiverPoint *__restrict__ pts, int npts,
+                                        float *__restrict__ rec_row)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npts) return;
+    const ReceiverPoint r = pts[i];
+    float sum = 0.0f;
+#pragma unroll
+    for (int rx = 0; rx <= 1; ++rx)
+#pragma unroll
+        for (int ry = 0; ry <= 1; ++ry)
+#pragma unroll
+            for (int rz = 0; rz <= 1; ++rz) {
+                if (!((r.mask >> (rx * 4 + ry * 2 + rz)) & 1u)) continue;
+                // r*p + (1 - r)*(1 - p) with r in {0, 1} is exactly p or 1 - p (x + 0 == x for the x >= 0 that occur)
+                const float wx = rx ? r.fx : __fsub_rn(1.0f, r.fx);
+                const float wy = ry ? r.fy : __fsub_rn(1.0f, r.fy);
+                const float wz = rz ? r.fz : __fsub_rn(1.0f, r.fz);
+                const float v = u[((long long)(r.X + rx) * g.nyp + (r.Y + ry)) * g.nzp + (r.Z + rz)];
+                sum = __fadd_rn(sum, __fmul_rn(__fmul_rn(__fmul_rn(wx, wy), wz), v));
+            }
+    rec_row[r.index] = sum;
+}
+
+int launch_sample_receivers(const float *u_level, const Grid &g, const ReceiverPoint *pts, int npts, float *rec_row,
+                            cudaStream_t stream)
+{
+    if (npts <= 0) return 0;
+    sample_receivers_kernel<<<(npts + 127) / 128, 128, 0, stream>>>(u_level, g, pts, npts, rec_row);
+    return (int)cudaGetLastError();
+}
+
 // ---------------------------------------------------------------------------- Section1 scatter
 __global__ void scatter_kernel(float *__restrict__ u2, Grid g, const SourceCell *__restrict__ cells, int ncells,
                                SourceView sv)

@@ -100,6 +100,10 @@ def lib():
         fn.restype, fn.argtypes = i, _KERNEL_ARGTYPES
     L.FDTD_SetRuntimeConfig.restype, L.FDTD_SetRuntimeConfig.argtypes = None, [i, i, i]
     L.fdtd_b200_plan_create.restype, L.fdtd_b200_plan_create.argtypes = i, [C.POINTER(Geometry), C.POINTER(vp)]
+    L.fdtd_b200_plan_create_order.restype, L.fdtd_b200_plan_create_order.argtypes = i, [C.POINTER(Geometry), i, C.POINTER(vp)]
+    L.fdtd_b200_plan_set_receivers.restype, L.fdtd_b200_plan_set_receivers.argtypes = i, [vp, vp, i, i]
+    L.fdtd_b200_plan_download_receivers.restype = i
+    L.fdtd_b200_plan_download_receivers.argtypes = [vp, vp, C.POINTER(i), C.POINTER(i)]
     L.fdtd_b200_plan_destroy.restype, L.fdtd_b200_plan_destroy.argtypes = i, [vp]
     L.fdtd_b200_plan_u.restype, L.fdtd_b200_plan_u.argtypes = vp, [vp]
     L.fdtd_b200_plan_m.restype, L.fdtd_b200_plan_m.argtypes = vp, [vp]
@@ -145,7 +149,8 @@ def exported_symbols():
     """Every entry point include/fdtd_b200.h declares (checked against the .so by the CPU tests)."""
     return [
         "Kernel_CUDA_Optimized", "Kernel_B200", "FDTD_SetRuntimeConfig",
-        "fdtd_b200_plan_create", "fdtd_b200_plan_destroy", "fdtd_b200_plan_u", "fdtd_b200_plan_m",
+        "fdtd_b200_plan_create", "fdtd_b200_plan_create_order", "fdtd_b200_plan_set_receivers", "fdtd_b200_plan_download_receivers",
+        "fdtd_b200_plan_destroy", "fdtd_b200_plan_u", "fdtd_b200_plan_m",
         "fdtd_b200_plan_level", "fdtd_b200_plan_probe_fuse", "fdtd_b200_plan_level_elems", "fdtd_b200_plan_upload", "fdtd_b200_plan_download", "fdtd_b200_plan_download_window", "fdtd_b200_plan_checksum", "fdtd_b200_plan_fill",
         "fdtd_b200_plan_fill_dense", "fdtd_b200_plan_set_sources", "fdtd_b200_plan_run", "fdtd_b200_plan_run_staged",
         "fdtd_b200_plan_last_launches", "fdtd_b200_plan_last_kernel_seconds", "fdtd_b200_plan_set_option",
@@ -281,14 +286,20 @@ class Plan:
     """One x-slab resident on one GPU (the whole grid when x_offset = 0 and nx_global = nx)."""
 
     def __init__(self, nx, ny, nz, *, dt=1e-3, h=(0.1, 0.1, 0.1), o=(0.0, 0.0, 0.0), x_offset=0, nx_global=None,
-                 deviceid=-1):
+                 deviceid=-1, space_order=4):
         h = (h, h, h) if np.isscalar(h) else h
         o = (o, o, o) if np.isscalar(o) else o
         self.geom = Geometry(nx, ny, nz, x_offset, nx if nx_global is None else nx_global, dt, h[0], h[1], h[2],
                              o[0], o[1], o[2], deviceid)
-        self.shape = (3, nx + 2 * HALO, ny + 2 * HALO, nz + 2 * HALO)
+        self.halo = space_order  # main.cpp:27-32: HALO == STENCIL_ORDER cells per side
+        self.shape = (3, nx + 2 * self.halo, ny + 2 * self.halo, nz + 2 * self.halo)
         self._h = C.c_void_p()
-        _check(lib().fdtd_b200_plan_create(C.byref(self.geom), C.byref(self._h)), "fdtd_b200_plan_create")
+        if space_order == HALO:
+            _check(lib().fdtd_b200_plan_create(C.byref(self.geom), C.byref(self._h)), "fdtd_b200_plan_create")
+        else:
+            _check(lib().fdtd_b200_plan_create_order(C.byref(self.geom), space_order, C.byref(self._h)),
+                   "fdtd_b200_plan_create_order")
+        self._nrec = 0
 
     def close(self):
         if self._h:
@@ -352,7 +363,8 @@ class Plan:
 
     def interior(self):
         """The window of the cells Section0 updates."""
-        return (HALO, self.shape[1] - HALO, HALO, self.shape[2] - HALO, HALO, self.shape[3] - HALO)
+        H = self.halo
+        return (H, self.shape[1] - H, H, self.shape[2] - H, H, self.shape[3] - H)
 
     def download_window(self, ring_level: int, window) -> np.ndarray:
         """One ring level on [x0,x1) x [y0,y1) x [z0,z1) (padded local coordinates) as a dense array."""
@@ -382,6 +394,23 @@ class Plan:
         _check(lib().fdtd_b200_plan_set_sources(self._h, src.ctypes.data, src.shape[0], src.shape[1],
                                                 coords.ctypes.data, coords.shape[0], coords.shape[1], p_src_m,
                                                 p_src_M), "fdtd_b200_plan_set_sources")
+
+    def set_receivers(self, coords):
+        """Receiver positions [nrec, >=3] in global physical coordinates; every run then records rec[time][r]."""
+        coords = np.ascontiguousarray(coords, np.float32).reshape(-1, 3) if coords is not None and len(coords) else None
+        self._nrec = 0 if coords is None else coords.shape[0]
+        _check(lib().fdtd_b200_plan_set_receivers(self._h, coords.ctypes.data if coords is not None else None, self._nrec,
+                                                  3), "fdtd_b200_plan_set_receivers")
+
+    def receivers(self):
+        """(rec [rows, nrec] float32, owned [nrec] bool) of the last run; owned marks the receivers THIS slab sampled."""
+        rows = C.c_int()
+        _check(lib().fdtd_b200_plan_download_receivers(self._h, None, None, C.byref(rows)), "fdtd_b200_plan_download_receivers")
+        rec = np.zeros((rows.value, self._nrec), np.float32)
+        owned = (C.c_int * max(1, self._nrec))()
+        _check(lib().fdtd_b200_plan_download_receivers(self._h, rec.ctypes.data if rec.size else None, owned, C.byref(rows)),
+               "fdtd_b200_plan_download_receivers")
+        return rec, np.array(owned[:self._nrec], bool)
 
     def run(self, time_m: int, time_M: int) -> Profiler:
         t = Profiler(0.0, 0.0)

@@ -49,6 +49,18 @@ def assemble(global_out: np.ndarray, slabs, parts):
     return global_out
 
 
+def merge_receivers(parts):
+    """[(rec [rows, nrec], owned [nrec]) per slab] -> rec [rows, nrec]: each receiver belongs to exactly one slab."""
+    rec = np.zeros_like(parts[0][0])
+    seen = np.zeros(rec.shape[1], int)
+    for r, owned in parts:
+        rec[:, owned] = r[:, owned]
+        seen += owned
+    if rec.shape[1] and not np.all(seen == 1):
+        raise ValueError("every receiver must be owned by exactly one slab")
+    return rec
+
+
 class SlabRun:
     """This rank's slab of a (nx_global, ny, nz) grid, neighbours attached through CUDA IPC."""
 
@@ -121,6 +133,14 @@ class LocalSlabs:
 
     def download(self, out):
         return assemble(out, [p.download() for p in self.plans], self.parts)
+
+    def set_receivers(self, coords):
+        for p in self.plans:
+            p.set_receivers(coords)
+
+    def receivers(self):
+        """Traces of the last run, every column taken from the slab that owns the receiver."""
+        return merge_receivers([p.receivers() for p in self.plans])
 
     def close(self):
         for p in reversed(self.plans):  # a slab may share the stream of the plan created before it

@@ -94,6 +94,15 @@ typedef struct {
 
 int fdtd_b200_plan_create(const fdtd_b200_geometry *geom, fdtd_b200_plan **out);
 int fdtd_b200_plan_destroy(fdtd_b200_plan *plan);
+/*
+ * The same at space order 4, 6, 8, 10 or 12.  The reference's driver is parameterised by
+ * STENCIL_ORDER with HALO == STENCIL_ORDER cells per side (main.cpp:2,27-32) but ships order-4 kernels only; here the
+ * arrays are u[3][nx+2*order][..][..], the stencil has radius order/2 with the standard central second-derivative
+ * weights (correctly rounded floats of the exact rationals; order 4 = the reference's literals) summed outermost pair
+ * first like openacc.cpp:104-106.  Orders above 4 run the one-point-per-thread kernel on a single slab
+ * (cudaErrorNotSupported for x-slabs).  Kernel_* reads the order off the padding, or from FDTD_B200_STENCIL_ORDER.
+ */
+int fdtd_b200_plan_create_order(const fdtd_b200_geometry *geom, int space_order, fdtd_b200_plan **out);
 
 /* Device pointers of the slab's arrays (for wrapping as torch tensors / IPC export). */
 float *fdtd_b200_plan_u(fdtd_b200_plan *plan);
@@ -147,6 +156,17 @@ int fdtd_b200_plan_fill_dense(fdtd_b200_plan *plan);
 int fdtd_b200_plan_set_sources(fdtd_b200_plan *plan, const float *src, int src_size0, int pstride,
                                const float *coords, int ncoords, int cstride, int p_src_m,
                                int p_src_M);
+
+/*
+ * Receivers (the reference has none -- the operator it was generated from samples them after the
+ * injection): rec[time][r] = sum over the in-range trilinear corners, x outermost / z innermost, of
+ * ((wx*wy)*wz)*u[time % 3][corner], positions / fractions / bounds exactly as the injection's (openacc.cpp:125-132).
+ * coords [nrec][cstride] in GLOBAL physical coordinates (copied).  Every run samples all its steps; the time is
+ * reported under section1.  download: host [rows][nrec] of the last run (rows = its steps, also returned), owned[r] = 1
+ * where THIS slab sampled receiver r (x-slabs: exactly one slab owns a receiver; the others leave 0).
+ */
+int fdtd_b200_plan_set_receivers(fdtd_b200_plan *plan, const float *coords, int nrec, int cstride);
+int fdtd_b200_plan_download_receivers(fdtd_b200_plan *plan, float *host, int *owned, int *rows);
 
 /*
  * Run time steps time_m..time_M inclusive on this slab (ring phase = time % 3).  The first

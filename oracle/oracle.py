@@ -75,10 +75,10 @@ def _ptr(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None and a.size else None
 
 
-def make_geom(nx, ny, nz, dt=1e-3, h=0.1, o=0.0) -> Geom:
+def make_geom(nx, ny, nz, dt=1e-3, h=0.1, o=0.0, halo=HALO) -> Geom:
     h = (h, h, h) if np.isscalar(h) else h
     o = (o, o, o) if np.isscalar(o) else o
-    return Geom(nx + 2 * HALO, ny + 2 * HALO, nz + 2 * HALO, 0, nx - 1, 0, ny - 1, 0, nz - 1,
+    return Geom(nx + 2 * halo, ny + 2 * halo, nz + 2 * halo, 0, nx - 1, 0, ny - 1, 0, nz - 1,
                 dt, h[0], h[1], h[2], o[0], o[1], o[2])
 
 
@@ -194,6 +194,56 @@ def run(u, m, src=None, coords=None, *, dt=1e-3, h=0.1, o=0.0, time_m=0, time_M=
         return t.section0, t.section1
 
     raise ValueError(impl)
+
+
+def fd_coeffs(space_order: int) -> np.ndarray:
+    """Second-derivative weights c[0..R] of space order 2R as this repo defines them (fdtd_oracle.c)."""
+    c = np.zeros(7, np.float32)
+    f = _lib("liboracle.so").oracle_fd_coeffs
+    f.restype, f.argtypes = C.c_int, [C.c_int, C.c_void_p]
+    R = f(space_order, _ptr(c))
+    if R < 0:
+        raise ValueError("space_order must be 4, 6, 8, 10 or 12")
+    return c[:R + 1]
+
+
+def run_order(u, m, src=None, coords=None, *, space_order=4, rec_coords=None, dt=1e-3, h=0.1, o=0.0, time_m=0,
+              time_M=None, p_src_m=0, p_src_M=None, threads=1):
+    """The operator at space order 2R (halo = space_order cells, so u is [3, nx + 2*so, ...]) with optional receiver
+    sampling.  Returns (section0_s, section1_s, rec) with rec float32 [T, nrec] or None.  Port only: the reference
+    has no kernels beyond order 4 and no receivers; at order 4 without receivers this equals run()."""
+    H = space_order
+    assert u.dtype == np.float32 and u.flags.c_contiguous and u.ndim == 4 and u.shape[0] == 3
+    assert m.dtype == np.float32 and m.flags.c_contiguous and m.shape == u.shape[1:]
+    nxp, nyp, nzp = u.shape[1:]
+    g = make_geom(nxp - 2 * H, nyp - 2 * H, nzp - 2 * H, dt, h, o, halo=H)
+    has_src = src is not None and coords is not None and src.size > 0
+    if has_src:
+        src, coords = _f32(src), _f32(coords)
+        p_src_M = coords.shape[0] - 1 if p_src_M is None else p_src_M
+        time_M = src.shape[0] - 1 if time_M is None else time_M
+    else:
+        p_src_M = -1
+        assert time_M is not None
+    T = time_M - time_m + 1
+    rec = None
+    if rec_coords is not None and len(rec_coords):
+        rec_coords = _f32(rec_coords)
+        rec = np.zeros((T, rec_coords.shape[0]), np.float32)
+    if threads > 1:
+        os.environ["OMP_NUM_THREADS"] = str(threads)
+    f = _lib("liboracle_omp.so" if threads > 1 else "liboracle.so").oracle_run_order
+    f.restype = C.c_int
+    f.argtypes = [C.POINTER(Geom), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                  C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_double)]
+    timers = (C.c_double * 2)(0.0, 0.0)
+    rc = f(C.byref(g), space_order, _ptr(m), _ptr(u), _ptr(src) if has_src else None, src.shape[0] if has_src else 0,
+           src.shape[1] if has_src else 1, _ptr(coords) if has_src else None, coords.shape[1] if has_src else 3,
+           p_src_m, p_src_M, time_m, time_M, _ptr(rec_coords) if rec is not None else None,
+           rec.shape[1] if rec is not None else 0, rec_coords.shape[1] if rec is not None else 3,
+           _ptr(rec) if rec is not None else None, timers)
+    assert rc == 0
+    return timers[0], timers[1], rec
 
 
 def section0(u0, u1, m, *, dt=1e-3, h=0.1):

@@ -107,3 +107,32 @@ def test_port_matches_compiled_reference(oracle):
         oracle.run(b, m, src, crd, impl="reference", time_m=2, time_M=T - 1)
         oracle.run(c, m, src, crd, impl="reference", time_m=2, time_M=T - 1, threads=3)
         assert bits_equal(a, b) and bits_equal(a, c)
+
+
+def test_order_generalisation_is_pinned_at_order_4(oracle):
+    """oracle_run_order (orders 4..12, receivers) is this repo's definition; at order 4 without
+    receivers it must be bit-identical to the pinned oracle_run, and its weights must be the reference's literals."""
+    rng = np.random.default_rng(3)
+    shape, T, S = (14, 11, 18), 9, 5
+    u = rng.uniform(-1, 1, (3,) + tuple(n + 8 for n in shape)).astype(np.float32)
+    m = rng.uniform(0.5, 3.0, u.shape[1:]).astype(np.float32)
+    src = rng.uniform(-20, 20, (T, S)).astype(np.float32)
+    crd = (rng.uniform(-0.04, 1.04, (S, 3)) * (np.array(shape, np.float32) - 1) * np.float32(0.1)).astype(np.float32)
+    a, b = u.copy(), u.copy()
+    oracle.run(a, m, src, crd)
+    _, _, rec = oracle.run_order(b, m, src, crd, space_order=4, rec_coords=crd)
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    assert rec.shape == (T, S) and np.isfinite(rec).all() and np.abs(rec).max() > 0
+    assert oracle.fd_coeffs(4).view(np.uint32).tolist() == [0xc0200000, 0x3faaaaab, 0xbdaaaaab]  # SURVEY 8a4 probe
+
+
+def test_fd_weights_are_consistent(oracle):
+    """Second-derivative consistency of every order: sum of weights 0, second moment 2, higher even moments 0."""
+    for so in (4, 6, 8, 10, 12):
+        c = oracle.fd_coeffs(so).astype(np.float64)
+        R = so // 2
+        k = np.arange(1, R + 1, dtype=np.float64)
+        assert abs(c[0] + 2 * c[1:].sum()) < 1e-6
+        assert abs(2 * (c[1:] * k ** 2).sum() - 2.0) < 1e-5
+        for p in range(2, R + 1):
+            assert abs((c[1:] * k ** (2 * p)).sum()) < 5e-3 * max(1.0, (np.abs(c[1:]) * k ** (2 * p)).sum())

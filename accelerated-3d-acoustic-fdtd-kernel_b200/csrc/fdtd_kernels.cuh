@@ -76,7 +76,10 @@ struct Tb2Step {
     const float *src_row2;             // src row of step n+1
     SlabLink link;                     // x-slab neighbours (all null for a single slab)
 };
-constexpr int kSlabEdgePlanes = 8;     // length of the boundary chunks of a slab with neighbours
+constexpr int kSlabEdgePlanes = 8;     // shortest slab side that can run linked two-step passes is 4 x this
+// Length of the two boundary chunks of a linked slab of nx planes (they are dispatched first and raise the neighbours'
+// flags): FDTD_B200_SLAB_EDGE overrides; 2*edge == nx means "no chunks in between" (the slabs then run in lock step).
+int slab_edge_planes(int nx, int xchunk, int tiles, int slots);
 int tb2_plan_build(Tb2Plan &p, float *u, const float *m, const Grid &g, const TmaConfig &cfg, bool exact, int sm_count);
 int launch_stencil_tb2(const Tb2Plan &p, const Tb2Step &a, bool exact, cudaStream_t stream);
 // 1 in *flag (device) unless the shells (every padded cell outside g's box) of levels 0..2 are bit-identical

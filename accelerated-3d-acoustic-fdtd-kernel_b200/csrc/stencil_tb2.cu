@@ -484,8 +484,8 @@ int launch_stencil_tb2(const Tb2Plan &p, const Tb2Step &a, bool exact, cudaStrea
     const bool linked = a.link.peer_u[0] != nullptr || a.link.peer_u[1] != nullptr;
     if (linked) {  // short boundary chunks hold the 4 planes a neighbour needs; the usual chunks lie in between
         if (nx < 4 * kSlabEdgePlanes) return (int)cudaErrorInvalidValue;
-        args.edge = kSlabEdgePlanes;
-        nchunks = 2 + (nx - 2 * kSlabEdgePlanes + p.xchunk - 1) / p.xchunk;
+        args.edge = slab_edge_planes(nx, p.xchunk, args.tiles_z * args.tiles_y, 0);
+        nchunks = 2 + (nx - 2 * args.edge + p.xchunk - 1) / p.xchunk;
         args.s.link.expect[0] = args.s.link.expect[1] = args.tiles_z * args.tiles_y;
     }
     dim3 grid(args.tiles_z * args.tiles_y, nchunks, 1);

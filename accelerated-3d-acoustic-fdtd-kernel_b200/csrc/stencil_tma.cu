@@ -26,6 +26,7 @@
 #include <cudaTypedefs.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 namespace fdtd {
 
@@ -326,6 +327,19 @@ static const Variant g_variants[] = {
 };
 static const int g_nvariants = (int)(sizeof(g_variants) / sizeof(g_variants[0]));
 
+int slab_edge_planes(int nx, int xchunk, int tiles, int slots)
+{
+    (void)xchunk; (void)tiles; (void)slots;
+    static const int forced = [] {
+        const char *v = getenv("FDTD_B200_SLAB_EDGE");
+        return (v && *v) ? atoi(v) : 0;
+    }();
+    int e = forced > 0 ? forced : kSlabEdgePlanes;
+    if (forced < 0) e = nx / 2;            // -1: two chunks of half a slab each
+    e = e < 4 ? 4 : e;
+    return e > nx / 2 ? nx / 2 : e;
+}
+
 bool tma_supported(const Grid &g)
 {
     return (g.nzp % 4 == 0) && (g.Z0 % 4 == 0) && ((g.Z1 - g.Z0) % 4 == 0) && (g.Z1 > g.Z0) && (g.Y1 > g.Y0);
@@ -455,8 +469,8 @@ int launch_stencil_tma(const TmaPlan &p, const StepArgs &a, bool exact, cudaStre
     int nchunks = (nx + p.xchunk - 1) / p.xchunk;
     const bool linked = a.link.peer_u[0] != nullptr || a.link.peer_u[1] != nullptr;
     if (linked && nx >= 4 * kSlabEdgePlanes) {  // short boundary chunks + the usual chunks in between
-        args.edge = kSlabEdgePlanes;
-        nchunks = 2 + (nx - 2 * kSlabEdgePlanes + p.xchunk - 1) / p.xchunk;
+        args.edge = slab_edge_planes(nx, p.xchunk, args.tiles_z * args.tiles_y, 0);
+        nchunks = 2 + (nx - 2 * args.edge + p.xchunk - 1) / p.xchunk;
     }
     dim3 grid(args.tiles_z * args.tiles_y, nchunks, 1);
     if (grid.y > 65535) return (int)cudaErrorInvalidValue;

@@ -76,6 +76,19 @@ struct Tb2Step {
     const float *src_row2;             // src row of step n+1
     SlabLink link;                     // x-slab neighbours (all null for a single slab)
 };
+// --- the same two-step pass as a time-step pipeline across a 2-CTA cluster (stencil_tc2.cu): CTA 0 computes u^{n+1}
+// and streams it into CTA 1's shared memory (DSMEM), CTA 1 computes u^{n+2}.  Unlinked slabs only.
+struct Tc2Plan {
+    alignas(64) CUtensorMap map_cur, map_prev, map_m;  // step 1: as Tb2Plan
+    alignas(64) CUtensorMap map_ctr, map_mc;           // step 2: u^n and m on the output tile, boxes (tz, ty)
+    int ty, tz, xchunk, variant;
+    int npairs;                                        // resident CTA pairs (SMs / 2): each loops over (tile, chunk) items
+    size_t smem_bytes;
+    bool valid = false;
+};
+int tc2_plan_build(Tc2Plan &p, float *u, const float *m, const Grid &g, const TmaConfig &cfg, bool exact, int sm_count);
+int launch_stencil_tc2(const Tc2Plan &p, const Tb2Step &a, bool exact, cudaStream_t stream);
+
 constexpr int kSlabEdgePlanes = 8;     // shortest slab side that can run linked two-step passes is 4 x this
 // Length of the two boundary chunks of a linked slab of nx planes (they are dispatched first and raise the neighbours'
 // flags): FDTD_B200_SLAB_EDGE overrides; 2*edge == nx means "no chunks in between" (the slabs then run in lock step).

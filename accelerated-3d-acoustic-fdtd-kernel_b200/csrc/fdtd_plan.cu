@@ -217,6 +217,7 @@ int fdtd::plan_create_internal(const PlanShape &s, fdtd_b200_plan **out, bool ca
     p->cfg.stages = env_int("FDTD_B200_STAGES", 0);
     p->cfg.xchunk = env_int("FDTD_B200_XCHUNK", 0);
     p->opt_t_fuse = env_int("FDTD_B200_T_FUSE", g_t_fuse);
+    p->opt_cluster = env_int("FDTD_B200_CLUSTER", 0);
     p->opt_stage_planes = env_int("FDTD_B200_STAGE_PLANES", -1);
 
     cudaError_t e = cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking);
@@ -709,6 +710,7 @@ static int *option_slot(fdtd_b200_plan *p, const char *key)
     if (!strcmp(key, "stages")) return &p->cfg.stages;
     if (!strcmp(key, "xchunk")) return &p->cfg.xchunk;
     if (!strcmp(key, "t_fuse_agreed")) return &p->t_fuse_agreed;
+    if (!strcmp(key, "cluster")) return &p->opt_cluster;
     if (!strcmp(key, "stage_planes")) return &p->opt_stage_planes;
     return nullptr;
 }
@@ -720,6 +722,7 @@ extern "C" int fdtd_b200_plan_set_option(fdtd_b200_plan *p, const char *key, int
     *slot = value;
     p->tma.valid = false;  // rebuilt lazily by the next run
     p->tb2.valid = false;
+    p->tc2.valid = false;
     return 0;
 }
 
@@ -727,6 +730,13 @@ extern "C" int fdtd_b200_plan_get_option(fdtd_b200_plan *p, const char *key, int
 {
     if (!p || !key || !value) return (int)cudaErrorInvalidValue;
     if (!strcmp(key, "kernel_used")) { *value = p->kernel_used; return 0; }
+    if (!strcmp(key, "cluster_used")) { *value = p->use_tc2 ? 1 : 0; return 0; }
+    if (p->t_fuse_used == 2 && p->use_tc2 && p->tc2.valid) {
+        if (!strcmp(key, "tile_y_used")) { *value = p->tc2.ty; return 0; }
+        if (!strcmp(key, "tile_z_used")) { *value = p->tc2.tz; return 0; }
+        if (!strcmp(key, "rows_used")) { *value = 1; return 0; }
+        if (!strcmp(key, "xchunk_used")) { *value = p->tc2.xchunk; return 0; }
+    }
     const bool two = p->t_fuse_used == 2 && p->tb2.valid;  // report the two-step kernel's shape when it is the one in use
     if (!strcmp(key, "t_fuse_used")) { *value = p->t_fuse_used; return 0; }
     if (!strcmp(key, "tile_y_used")) { *value = two ? p->tb2.ty : (p->tma.valid ? p->tma.ty : 0); return 0; }
@@ -833,7 +843,8 @@ static int plan_pass2(fdtd_b200_plan *p, int time, bool first_of_run)
     a.link.epoch = ++p->epoch;
     a.link.wait = first_of_run ? 0 : 1;
     a.link.depth = 4;
-    int rc = launch_stencil_tb2(p->tb2, a, p->opt_exact != 0, p->stream);
+    int rc = p->use_tc2 ? launch_stencil_tc2(p->tc2, a, p->opt_exact != 0, p->stream)
+                        : launch_stencil_tb2(p->tb2, a, p->opt_exact != 0, p->stream);
     if (rc) return rc;
     p->last_launches++;
     std::swap(p->phys[t1], p->work);
@@ -946,7 +957,12 @@ int fdtd::plan_prepare(fdtd_b200_plan *p)
         } else {
             depth = p->t_fuse_agreed >= 2 ? 2 : 1;
         }
-        if (depth == 2 && !p->tb2.valid) {
+        p->use_tc2 = depth == 2 && p->opt_cluster != 0 && !linked;
+        if (p->use_tc2 && !p->tc2.valid) {
+            int rc = tc2_plan_build(p->tc2, p->d_u, p->d_m, p->g, p->cfg, p->opt_exact != 0, p->sm_count);
+            if (rc) return rc;
+        }
+        if (depth == 2 && !p->use_tc2 && !p->tb2.valid) {
             int rc = tb2_plan_build(p->tb2, p->d_u, p->d_m, p->g, p->cfg, p->opt_exact != 0, p->sm_count);
             if (rc) return rc;
         }

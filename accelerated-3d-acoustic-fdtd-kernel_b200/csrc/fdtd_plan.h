@@ -75,6 +75,9 @@ struct fdtd_b200_plan {
     fdtd::TmaConfig cfg{};
     fdtd::TmaPlan tma{};
     fdtd::Tb2Plan tb2{};
+    fdtd::Tc2Plan tc2{};             // two-step passes on 2-CTA clusters (option "cluster", unlinked slabs)
+    int opt_cluster = 0;
+    bool use_tc2 = false;            // the current run's passes go through stencil_tc2
     int kernel_used = 0;
     int t_fuse_used = 1;             // time steps per pass of the current run (1 or 2)
     int t_fuse_agreed = -1;          // linked slabs: depth all slabs agreed on (-1 = not negotiated -> 1)

@@ -81,7 +81,7 @@ struct Tb2Step {
 struct Tc2Plan {
     alignas(64) CUtensorMap map_cur, map_prev, map_m;  // step 1: as Tb2Plan
     alignas(64) CUtensorMap map_ctr, map_mc;           // step 2: u^n and m on the output tile, boxes (tz, ty)
-    int ty, tz, xchunk, variant;
+    int ty, tz, rows, xchunk, variant;
     int npairs;                                        // resident CTA pairs (SMs / 2): each loops over (tile, chunk) items
     size_t smem_bytes;
     bool valid = false;

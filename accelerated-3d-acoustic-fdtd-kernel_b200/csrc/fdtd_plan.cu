@@ -720,6 +720,7 @@ extern "C" int fdtd_b200_plan_set_option(fdtd_b200_plan *p, const char *key, int
     int *slot = option_slot(p, key);
     if (!slot) return (int)cudaErrorInvalidValue;
     *slot = value;
+    if (slot == &p->opt_t_fuse) p->t_fuse_explicit = true;
     p->tma.valid = false;  // rebuilt lazily by the next run
     p->tb2.valid = false;
     p->tc2.valid = false;
@@ -734,7 +735,7 @@ extern "C" int fdtd_b200_plan_get_option(fdtd_b200_plan *p, const char *key, int
     if (p->t_fuse_used == 2 && p->use_tc2 && p->tc2.valid) {
         if (!strcmp(key, "tile_y_used")) { *value = p->tc2.ty; return 0; }
         if (!strcmp(key, "tile_z_used")) { *value = p->tc2.tz; return 0; }
-        if (!strcmp(key, "rows_used")) { *value = 1; return 0; }
+        if (!strcmp(key, "rows_used")) { *value = p->tc2.rows; return 0; }
         if (!strcmp(key, "xchunk_used")) { *value = p->tc2.xchunk; return 0; }
     }
     const bool two = p->t_fuse_used == 2 && p->tb2.valid;  // report the two-step kernel's shape when it is the one in use
@@ -867,6 +868,10 @@ static int plan_fuse_feasible(fdtd_b200_plan *p, int *out)
 {
     *out = 1;
     if (p->opt_t_fuse < 2 || p->opt_kernel == 1 || p->shape.space_order != 4 || !tma_supported(p->g)) return 0;
+    // In bit-exact arithmetic a two-step pass is SLOWER than two one-step launches (245 vs 393 Gpts/s at 512^3: the IEEE
+    // division and the unfused chain make the pass issue-bound).  The driver's FDTD_TFUSE (main.cpp:266-276) is a request
+    // for speed, not for a schedule: with exact arithmetic it is honoured only when set explicitly through set_option.
+    if (p->opt_exact && !p->t_fuse_explicit) return 0;
     const bool linked = p->link.peer_u[0] || p->link.peer_u[1];
     // receivers on linked slabs read a ghost plane of u^{n+1} that the neighbour's SAME pass writes: one-step passes
     // (nrec_total is the same on every slab, so all slabs decide alike)

@@ -77,6 +77,7 @@ struct fdtd_b200_plan {
     fdtd::Tb2Plan tb2{};
     fdtd::Tc2Plan tc2{};             // two-step passes on 2-CTA clusters (option "cluster", unlinked slabs)
     int opt_cluster = 0;
+    bool t_fuse_explicit = false;    // "t_fuse" came from set_option (honoured as is) rather than from the driver's hook / env
     bool use_tc2 = false;            // the current run's passes go through stencil_tc2
     int kernel_used = 0;
     int t_fuse_used = 1;             // time steps per pass of the current run (1 or 2)

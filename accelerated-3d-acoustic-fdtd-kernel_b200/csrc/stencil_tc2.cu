@@ -24,6 +24,7 @@
 #include "tma_ptx.cuh"
 
 #include <math.h>
+#include <stdlib.h>
 
 namespace fdtd {
 
@@ -37,13 +38,14 @@ struct Tc2Args {
     int tiles_z, tiles_y, xchunk, nchunks;
 };
 
-template <int TY_, int TZ_>
+template <int TY_, int TZ_, int RY_>
 struct Tc2Shape {
-    static constexpr int TY = TY_, TZ = TZ_;
+    static constexpr int TY = TY_, TZ = TZ_, RY = RY_;    // RY = rows per consumer thread (1 or 2)
     static constexpr int ER = TY + 4, EC = TZ / 4 + 2;   // extended tile: rows, float4 columns
     static constexpr int HP = 4 * EC;                     // pitch of every extended-tile slot (floats)
-    static constexpr int NCA = ER * EC;                   // A: one consumer thread per float4 column of the extended tile
-    static constexpr int NCB = TY * (TZ / 4);             // B: one per float4 column of the output tile
+    static_assert(TY % RY == 0 && ER % RY == 0 && (RY == 1 || RY == 2), "rows per thread must divide both tiles");
+    static constexpr int NCA = (ER / RY) * EC;            // A: one consumer thread per RY rows x one float4 column of the extended tile
+    static constexpr int NCB = (TY / RY) * (TZ / 4);      // B: the same on the output tile
     static constexpr int NWA = (NCA + 31) / 32, NWB = (NCB + 31) / 32;
     static constexpr int NC = NWA * 32, NT = NC + 32;     // + one producer warp (both roles)
     // rings: u^n (A; 4 of its slots are the x look-ahead of the stencil, the rest is prefetch), u^{n-1} and m (A; they become
@@ -124,10 +126,10 @@ __device__ __forceinline__ void tc2_inject_plane(float4 &r, int X, int Y, int Z,
     }
 }
 
-template <int TY, int TZ, bool EXACT>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Tc2Shape<TY, TZ>::NT, 1) stencil_tc2_kernel(const __grid_constant__ Tc2Args a)
+template <int TY, int TZ, int RY, bool EXACT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Tc2Shape<TY, TZ, RY>::NT, 1) stencil_tc2_kernel(const __grid_constant__ Tc2Args a)
 {
-    using T = Tc2Shape<TY, TZ>;
+    using T = Tc2Shape<TY, TZ, RY>;
     constexpr int SU = T::SU, SP = T::SP, SB = T::SB, SC = T::SC, HP = T::HP, ER = T::ER, EC = T::EC;
     constexpr int USLOT_F = T::USLOT / 4, CSLOT_F = T::CSLOT / 4, TILE_F = TY * TZ;
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -205,13 +207,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Tc2Shape<TY, TZ>::NT
             }
         } else {
             const bool active = threadIdx.x < T::NCA;
-            const int er = active ? threadIdx.x / EC : 0, ec = active ? threadIdx.x % EC : 0;
+            const int er = active ? (threadIdx.x / EC) * RY : 0, ec = active ? threadIdx.x % EC : 0;  // first of this thread's rows
             const int ownU = (er + 2) * HP + 4 * ec;  // own column in a u^n slot (rows start at Yt-4)
             const int ownC = er * HP + 4 * ec;        // own column in an extended-tile slot (rows start at Yt-2)
             const uint32_t r_own = r_ring0 + 4u * (uint32_t)ownC;
-            // bytes this warp sends per plane: 16 per active lane (the last warp of the extended tile is partly idle)
+            // bytes this warp sends per plane: 16 per row of an active lane (the last warp of the extended tile is partly idle)
             const int warp_first = (int)(threadIdx.x & ~31u);
-            const uint32_t warp_bytes = 16u * (uint32_t)max(0, min(32, T::NCA - warp_first));
+            const uint32_t warp_bytes = 16u * RY * (uint32_t)max(0, min(32, T::NCA - warp_first));
             int us = 0, pp = 0, b8 = 0;   // running slots: next u^n stage to read, u^{n-1} / m, the partner's ring
             uint32_t upar = 0;            // parity of the ring use `us` is in
             uint32_t fpar = 0;            // parity to wait for on bfree[b8] from the second ring use on
@@ -223,19 +225,27 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Tc2Shape<TY, TZ>::NT
                 const int Yt = g.Y0 + (tile / a.tiles_z) * TY, Zt = g.Z0 + (tile % a.tiles_z) * TZ;
                 const int nit = np + 4;  // step-1 planes Xa-2 .. Xb+1
                 const int Y = Yt - 2 + er, Z = Zt - 4 + 4 * ec;
-                const bool inb = active && Z >= g.Z0 && Z < g.Z1 && Y >= g.Y0 && Y < g.Y1;   // interior in (y,z)
-                const bool core = inb && er >= 2 && er < ER - 2 && ec >= 1 && ec < EC - 1;   // inside the output tile
+                const bool z_in = active && Z >= g.Z0 && Z < g.Z1;
+                const bool rows_core = er >= 2 && er < ER - 2 && ec >= 1 && ec < EC - 1;  // rows of the output tile (2 | RY-aligned)
+                bool inb[RY], core[RY], any_inb = false;
+#pragma unroll
+                for (int r = 0; r < RY; ++r) {
+                    inb[r] = z_in && Y + r >= g.Y0 && Y + r < g.Y1;  // interior in (y,z)
+                    core[r] = inb[r] && rows_core;                    // inside the output tile
+                    any_inb |= inb[r];
+                }
                 bool chunk_has_src = false;
                 if (sv.ncells > 0) chunk_has_src = (sv.plane_off[min(Xb + 2, g.nxp)] - sv.plane_off[max(Xa - 2, 0)]) > 0;
                 float *__restrict__ out1 = a.s.u + (long long)a.s.l_n1 * g.lvl + (long long)(Xa - 2) * plane + (long long)Y * g.nzp + Z;
 
                 // prologue: stages 0..3 of the item; stages 0 and 1 are never a centre plane and go back at once
-                float4 qU[5];
+                float4 qU[5][RY];
                 int uc = us;  // slot of the item's stage 0; after the prologue it trails `us` by two stages (the centre plane)
 #pragma unroll
                 for (int s = 0; s < 4; ++s) {
                     mbar_wait(full0 + 8 * us, upar);
-                    qU[s] = lds128(sU + us * USLOT_F + ownU);
+#pragma unroll
+                    for (int r = 0; r < RY; ++r) qU[s][r] = lds128(sU + us * USLOT_F + ownU + r * HP);
                     if (s < 2) {
                         __syncwarp();
                         if (lane == 0) mbar_arrive(empty0 + 8 * us);
@@ -252,24 +262,41 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Tc2Shape<TY, TZ>::NT
                         const int i = i0 + k;
                         if (i >= nit) break;
                         mbar_wait(full0 + 8 * us, upar);   // front stage i+4
-                        qU[(k + 4) % 5] = lds128(sU + us * USLOT_F + ownU);
+#pragma unroll
+                        for (int r = 0; r < RY; ++r) qU[(k + 4) % 5][r] = lds128(sU + us * USLOT_F + ownU + r * HP);
                         const int P1 = Xa - 2 + i;
-                        float4 res = qU[(k + 2) % 5];  // halo cells keep their value (identical in every level by construction)
-                        if (inb && P1 >= g.X0 && P1 < g.X1) {
+                        float4 res[RY];  // halo cells keep their value (identical in every level by construction)
+#pragma unroll
+                        for (int r = 0; r < RY; ++r) res[r] = qU[(k + 2) % 5][r];
+                        if (any_inb && P1 >= g.X0 && P1 < g.X1) {
                             const float *P = sU + uc * USLOT_F + ownU;
-                            const float4 ym2 = lds128(P - 2 * HP), ym1 = lds128(P - HP), yp1 = lds128(P + HP), yp2 = lds128(P + 2 * HP);
-                            const float2 zl = lds64(P - 2), zr = lds64(P + 4);
-                            const float4 pv = lds128(sP + pp * CSLOT_F + ownC);
-                            const float4 mv = lds128(sM + pp * CSLOT_F + ownC);
-                            res = column4<EXACT>(qU[(k + 2) % 5], qU[k % 5], qU[(k + 1) % 5], qU[(k + 3) % 5], qU[(k + 4) % 5], ym2, ym1,
-                                                 yp1, yp2, zl, zr, pv, mv, a.s.k);
-                            if (chunk_has_src) tc2_inject_plane(res, P1, Y, Z, sv);  // rare: source cells of step n (ghost zone too)
-                            if (core && P1 >= Xa && P1 < Xb) *reinterpret_cast<float4 *>(out1) = res;
+                            // this thread's y column on the centre plane: 2 rows above, own rows (registers), 2 rows below
+                            float4 col[RY + 4];
+                            col[0] = lds128(P - 2 * HP);
+                            col[1] = lds128(P - HP);
+                            col[RY + 2] = lds128(P + RY * HP);
+                            col[RY + 3] = lds128(P + (RY + 1) * HP);
+#pragma unroll
+                            for (int r = 0; r < RY; ++r) col[r + 2] = qU[(k + 2) % 5][r];
+#pragma unroll
+                            for (int r = 0; r < RY; ++r) {
+                                const float2 zl = lds64(P + r * HP - 2), zr = lds64(P + r * HP + 4);
+                                const float4 pv = lds128(sP + pp * CSLOT_F + ownC + r * HP);
+                                const float4 mv = lds128(sM + pp * CSLOT_F + ownC + r * HP);
+                                float4 v = column4<EXACT>(col[r + 2], qU[k % 5][r], qU[(k + 1) % 5][r], qU[(k + 3) % 5][r], qU[(k + 4) % 5][r],
+                                                          col[r], col[r + 1], col[r + 3], col[r + 4], zl, zr, pv, mv, a.s.k);
+                                if (chunk_has_src) tc2_inject_plane(v, P1, Y + r, Z, sv);  // rare: source cells of step n (ghost zone too)
+                                if (inb[r]) res[r] = v;
+                                if (core[r] && P1 >= Xa && P1 < Xb) *reinterpret_cast<float4 *>(out1 + r * g.nzp) = v;
+                            }
                         }
                         out1 += plane;
                         // the step-1 plane goes into the next slot of the partner's ring
                         if (lapped) mbar_wait(bfree0 + 8 * b8, fpar);
-                        if (active) st_async_v4(r_own + (uint32_t)(b8 * T::CSLOT), res, r_bfull0 + 8 * b8);
+                        if (active) {
+#pragma unroll
+                            for (int r = 0; r < RY; ++r) st_async_v4(r_own + (uint32_t)(b8 * T::CSLOT + r * HP * 4), res[r], r_bfull0 + 8 * b8);
+                        }
                         __syncwarp();
                         if (lane == 0) {
                             mbar_arrive_expect_tx_remote(r_bfull0 + 8 * b8, warp_bytes);  // this warp's part of the plane is on its way
@@ -326,7 +353,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Tc2Shape<TY, TZ>::NT
         } else if (threadIdx.x < T::NWB * 32) {
             const bool active = threadIdx.x < T::NCB;
             constexpr int ZQ = TZ / 4;
-            const int yr = active ? threadIdx.x / ZQ : 0, zq = active ? threadIdx.x % ZQ : 0;
+            const int yr = active ? (threadIdx.x / ZQ) * RY : 0, zq = active ? threadIdx.x % ZQ : 0;  // first of this thread's rows
             const int ownC = (yr + 2) * HP + 4 * (zq + 1);  // own column in an extended-tile slot
             const int ctr = yr * TZ + 4 * zq;               // own column in a centre tile
             SourceView sv2 = sv;
@@ -339,18 +366,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Tc2Shape<TY, TZ>::NT
                 const int Xa = g.X0 + chunk * a.xchunk, Xb = min(g.X1, Xa + a.xchunk), np = Xb - Xa;
                 const int Yt = g.Y0 + (tile / a.tiles_z) * TY, Zt = g.Z0 + (tile % a.tiles_z) * TZ;
                 const int Y = Yt + yr, Z = Zt + 4 * zq;
-                const bool ok = active && Y < g.Y1 && Z < g.Z1;
+                const bool z_ok = active && Z < g.Z1;
                 bool chunk_has_src = false;
                 if (sv.ncells > 0) chunk_has_src = (sv.plane_off[Xb] - sv.plane_off[Xa]) > 0;
                 float *__restrict__ out2 = a.s.u + (long long)a.s.l_n2 * g.lvl + (long long)Xa * plane + (long long)Y * g.nzp + Z;
 
-                // qR[j % 5] = own column of the item's step-1 plane j (A's iteration j, plane Xa-2+j)
-                float4 qR[5];
+                // qR[j % 5] = own rows of the item's step-1 plane j (A's iteration j, plane Xa-2+j)
+                float4 qR[5][RY];
                 int c8 = f8;  // slot of the item's plane 0; after the prologue it trails `f8` by two planes (the centre plane)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     mbar_wait(bfull0 + 8 * f8, fpar);
-                    qR[j] = lds128(sB + f8 * CSLOT_F + ownC);
+#pragma unroll
+                    for (int r = 0; r < RY; ++r) qR[j][r] = lds128(sB + f8 * CSLOT_F + ownC + r * HP);
                     if (j < 2) {  // planes 0 and 1 are never a centre plane: hand their slots back now
                         __syncwarp();
                         if (lane == 0) mbar_arrive_remote(r_bfree0 + 8 * f8);
@@ -367,22 +395,38 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Tc2Shape<TY, TZ>::NT
                         const int i = i0 + k;
                         if (i >= np) break;
                         mbar_wait(bfull0 + 8 * f8, fpar);  // front plane i+4
-                        qR[(k + 4) % 5] = lds128(sB + f8 * CSLOT_F + ownC);
+#pragma unroll
+                        for (int r = 0; r < RY; ++r) qR[(k + 4) % 5][r] = lds128(sB + f8 * CSLOT_F + ownC + r * HP);
                         const float *P = sB + c8 * CSLOT_F + ownC;
-                        const float4 ym2 = lds128(P - 2 * HP), ym1 = lds128(P - HP), yp1 = lds128(P + HP), yp2 = lds128(P + 2 * HP);
-                        const float2 zl = lds64(P - 2), zr = lds64(P + 4);
+                        float4 col[RY + 4];
+                        col[0] = lds128(P - 2 * HP);
+                        col[1] = lds128(P - HP);
+                        col[RY + 2] = lds128(P + RY * HP);
+                        col[RY + 3] = lds128(P + (RY + 1) * HP);
+                        float2 zl[RY], zr[RY];
+#pragma unroll
+                        for (int r = 0; r < RY; ++r) zl[r] = lds64(P + r * HP - 2), zr[r] = lds64(P + r * HP + 4);
                         mbar_wait(cfull0 + 8 * cs, cpar);
-                        const float4 pv = lds128(sV + cs * TILE_F + ctr);
-                        const float4 mv = lds128(sMB + cs * TILE_F + ctr);
+                        float4 pv[RY], mv[RY];
+#pragma unroll
+                        for (int r = 0; r < RY; ++r) {
+                            pv[r] = lds128(sV + cs * TILE_F + ctr + r * TZ);
+                            mv[r] = lds128(sMB + cs * TILE_F + ctr + r * TZ);
+                        }
                         __syncwarp();
                         if (lane == 0) {
                             mbar_arrive_remote(r_bfree0 + 8 * c8);  // A may overwrite the slot of step-1 plane i+2
                             mbar_arrive(cempty0 + 8 * cs);
                         }
-                        float4 o = column4<EXACT>(qR[(k + 2) % 5], qR[k % 5], qR[(k + 1) % 5], qR[(k + 3) % 5], qR[(k + 4) % 5], ym2, ym1,
-                                                  yp1, yp2, zl, zr, pv, mv, a.s.k);
-                        if (chunk_has_src) tc2_inject_plane(o, Xa + i, Y, Z, sv2);  // source cells of step n+1
-                        if (ok) *reinterpret_cast<float4 *>(out2) = o;
+#pragma unroll
+                        for (int r = 0; r < RY; ++r) col[r + 2] = qR[(k + 2) % 5][r];
+#pragma unroll
+                        for (int r = 0; r < RY; ++r) {
+                            float4 o = column4<EXACT>(col[r + 2], qR[k % 5][r], qR[(k + 1) % 5][r], qR[(k + 3) % 5][r], qR[(k + 4) % 5][r], col[r],
+                                                      col[r + 1], col[r + 3], col[r + 4], zl[r], zr[r], pv[r], mv[r], a.s.k);
+                            if (chunk_has_src) tc2_inject_plane(o, Xa + i, Y + r, Z, sv2);  // source cells of step n+1
+                            if (z_ok && Y + r < g.Y1) *reinterpret_cast<float4 *>(out2 + r * g.nzp) = o;
+                        }
                         out2 += plane;
                         if (++f8 == SB) {
                             f8 = 0;
@@ -411,19 +455,31 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Tc2Shape<TY, TZ>::NT
 // ---------------------------------------------------------------------------- host side
 typedef void (*Tc2KernelFn)(const Tc2Args);
 struct Tc2Variant {
-    int ty, tz;
+    int ty, tz, rows;
     bool exact;
     Tc2KernelFn fn;
     int nt;
     size_t smem;
 };
-#define FDTD_TC2_1(TY_, TZ_, EX_) {TY_, TZ_, EX_, stencil_tc2_kernel<TY_, TZ_, EX_>, Tc2Shape<TY_, TZ_>::NT, (size_t)Tc2Shape<TY_, TZ_>::SMEM}
-#define FDTD_TC2(TY_, TZ_) FDTD_TC2_1(TY_, TZ_, false), FDTD_TC2_1(TY_, TZ_, true)
+#define FDTD_TC2_1(TY_, TZ_, RY_, EX_) \
+    {TY_, TZ_, RY_, EX_, stencil_tc2_kernel<TY_, TZ_, RY_, EX_>, Tc2Shape<TY_, TZ_, RY_>::NT, (size_t)Tc2Shape<TY_, TZ_, RY_>::SMEM}
+#define FDTD_TC2(TY_, TZ_, RY_) FDTD_TC2_1(TY_, TZ_, RY_, false), FDTD_TC2_1(TY_, TZ_, RY_, true)
 static const Tc2Variant g_tc2[] = {
-    // output tile; first match that divides the grid wins (else the first)
-    FDTD_TC2(16, 128), FDTD_TC2(32, 64), FDTD_TC2(28, 64), FDTD_TC2(24, 64), FDTD_TC2(16, 64), FDTD_TC2(12, 128),
+    // output tile, rows per thread; the first match that divides the grid wins (else the first match)
+    FDTD_TC2(16, 128, 2), FDTD_TC2(32, 64, 2), FDTD_TC2(16, 128, 1), FDTD_TC2(32, 64, 1), FDTD_TC2(28, 64, 1), FDTD_TC2(24, 64, 1),
+    FDTD_TC2(28, 64, 2), FDTD_TC2(24, 64, 2), FDTD_TC2(16, 64, 1), FDTD_TC2(12, 128, 1), FDTD_TC2(40, 64, 2),
 };
 static const int g_ntc2 = (int)(sizeof(g_tc2) / sizeof(g_tc2[0]));
+
+// FDTD_B200_TC2_PAIRS: resident CTA pairs (default SMs / 2); -1 = one pair per item (no persistence)
+static int env_pairs()
+{
+    static const int v = [] {
+        const char *e = getenv("FDTD_B200_TC2_PAIRS");
+        return (e && *e) ? atoi(e) : 0;
+    }();
+    return v;
+}
 
 int tc2_plan_build(Tc2Plan &p, float *u, const float *m, const Grid &g, const TmaConfig &cfg, bool exact, int sm_count)
 {
@@ -434,6 +490,7 @@ int tc2_plan_build(Tc2Plan &p, float *u, const float *m, const Grid &g, const Tm
     for (int pass = 0; pass < 2 && vi < 0; ++pass)
         for (int i = 0; i < g_ntc2 && vi < 0; ++i)
             if (g_tc2[i].exact == exact && (cfg.ty <= 0 || g_tc2[i].ty == cfg.ty) && (cfg.tz <= 0 || g_tc2[i].tz == cfg.tz) &&
+                (cfg.rows <= 0 || g_tc2[i].rows == cfg.rows) &&
                 (pass == 1 || cfg.ty > 0 || cfg.tz > 0 || (ny % g_tc2[i].ty == 0 && nz % g_tc2[i].tz == 0)))
                 vi = i;
     if (vi < 0) return (int)cudaErrorInvalidValue;
@@ -471,7 +528,8 @@ int tc2_plan_build(Tc2Plan &p, float *u, const float *m, const Grid &g, const Tm
     }
     p.ty = v.ty;
     p.tz = v.tz;
-    p.npairs = sm_count / 2;
+    p.rows = v.rows;
+    p.npairs = env_pairs() > 0 ? env_pairs() : (env_pairs() < 0 ? 1 << 30 : sm_count / 2);
     p.xchunk = xchunk;
     p.variant = vi;
     p.smem_bytes = v.smem;

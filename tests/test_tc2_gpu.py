@@ -9,18 +9,19 @@ from test_tb2_gpu import REL_L2_TOL, fused_case, run_plan
 
 pytestmark = pytest.mark.gpu
 
-TILES = [(28, 64), (24, 64), (32, 64), (16, 128), (16, 64), (12, 128)]
+TILES = [(28, 64, 1), (24, 64, 1), (32, 64, 1), (16, 128, 1), (16, 64, 1), (12, 128, 1), (16, 128, 2), (32, 64, 2), (28, 64, 2),
+         (24, 64, 2), (40, 64, 2)]  # output tile, rows per thread
 
 
-@pytest.mark.parametrize("ty,tz", TILES)
-def test_cluster_pass_bit_exact(pkg, oracle, ty, tz):
+@pytest.mark.parametrize("ty,tz,rows", TILES)
+def test_cluster_pass_bit_exact(pkg, oracle, ty, tz, rows):
     """Every instantiation on a grid that is not a multiple of the tile, several x chunks (some shorter than the ring),
     random m, sources incl. coincident ones."""
     shape, T, S = (23, 44, 72), 11, 6
     u, m, src, crd = fused_case(300 + ty + tz, shape, T, S)
     ref = u.copy()
     oracle.run(ref, m, src, crd, impl="port")
-    opts = {"kernel": 2, "t_fuse": 2, "cluster": 1, "tile_y": ty, "tile_z": tz, "xchunk": 9}
+    opts = {"kernel": 2, "t_fuse": 2, "cluster": 1, "tile_y": ty, "tile_z": tz, "rows": rows, "xchunk": 9}
     out, t, info = run_plan(pkg, u, m, src, crd, options=dict(opts, exact=1))
     assert info["t_fuse_used"] == 2 and (info["tile_y_used"], info["tile_z_used"]) == (ty, tz)
     assert info["launches"] < T + 1

@@ -74,7 +74,15 @@ struct SlabLink {
     int epoch;               // sequence number of this step (same on every slab)
     int wait;                // 1: ghost planes of u[t0] were produced by the neighbours' step epoch-1
     int depth;               // boundary planes pushed per side: 2 (one step per pass), 4 when two-step passes are in use
+    // Per-tile completion flags (one int per (y,z) tile and side, in the tail of every slab's u allocation): a boundary CTA
+    // stores the launch's epoch into the NEIGHBOUR's array when it is done (boundary planes stored, ghost planes read).  When
+    // the previous launch had the same kernel and tile grid (tile_mode), a boundary CTA waits only for the 3 x 3 tiles around
+    // its own instead of for the whole boundary, so slabs need neither short boundary chunks nor lock step.
+    int *my_tile[2];         // arrays in this slab's memory raised by the neighbours
+    int *peer_tile[2];       // arrays in the neighbours' memory that THIS slab raises
+    int tile_mode;           // 1: wait on my_tile[side][3x3 around the tile] >= epoch-1 instead of my_flag[side]
 };
+constexpr int kMaxFlagTiles = 16384;  // tiles per side the per-tile flag arrays can hold
 
 // Field geometry of one slab as the kernels see it.
 struct Grid {

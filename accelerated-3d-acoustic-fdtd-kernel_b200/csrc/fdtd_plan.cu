@@ -223,7 +223,9 @@ int fdtd::plan_create_internal(const PlanShape &s, fdtd_b200_plan **out, bool ca
     cudaError_t e = cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking);
     p->flags_offset = (FDTD_LEVELS * (size_t)p->g.lvl * sizeof(float) + 255) / 256 * 256;
     p->arena_offset = p->flags_offset + 256;
-    p->u_bytes = p->arena_offset + kArenaBytes;
+    p->tile_flags_offset = p->arena_offset + kArenaBytes;
+    p->u_bytes = p->tile_flags_offset + 2 * (size_t)kMaxFlagTiles * sizeof(int);
+    p->opt_tile_flags = env_int("FDTD_B200_TILE_FLAGS", 1);
     p->m_bytes = (size_t)p->g.lvl * sizeof(float);
     const char *nc = getenv("FDTD_B200_NO_CACHE");
     p->cache_buffers = cache_buffers && !(nc && *nc == '1');
@@ -236,6 +238,10 @@ int fdtd::plan_create_internal(const PlanShape &s, fdtd_b200_plan **out, bool ca
         p->link.my_flag[1] = p->d_flags + 1;
         p->link.counter = p->d_flags + 2;
         p->link.err = p->d_flags + 4;
+        int *tf = reinterpret_cast<int *>(reinterpret_cast<char *>(p->d_u) + p->tile_flags_offset);
+        p->link.my_tile[0] = tf;
+        p->link.my_tile[1] = tf + kMaxFlagTiles;
+        if (e == cudaSuccess) e = cudaMemset(tf, 0, 2 * (size_t)kMaxFlagTiles * sizeof(int));
     }
     if (e == cudaSuccess && !reused) e = cudaMalloc(&p->d_m, p->m_bytes);
     if (e != cudaSuccess) {
@@ -711,6 +717,7 @@ static int *option_slot(fdtd_b200_plan *p, const char *key)
     if (!strcmp(key, "xchunk")) return &p->cfg.xchunk;
     if (!strcmp(key, "t_fuse_agreed")) return &p->t_fuse_agreed;
     if (!strcmp(key, "cluster")) return &p->opt_cluster;
+    if (!strcmp(key, "tile_flags")) return &p->opt_tile_flags;
     if (!strcmp(key, "stage_planes")) return &p->opt_stage_planes;
     return nullptr;
 }
@@ -756,6 +763,12 @@ extern "C" int fdtd_b200_plan_get_option(fdtd_b200_plan *p, const char *key, int
 }
 
 // ---------------------------------------------------------------------------- the time loop
+static int tile_count_tma(const fdtd_b200_plan *p)
+{
+    if (!p->tma.valid) return 1 << 30;
+    return ((p->g.Y1 - p->g.Y0 + p->tma.ty - 1) / p->tma.ty) * ((p->g.Z1 - p->g.Z0 + p->tma.tz - 1) / p->tma.tz);
+}
+
 // One time step on [X0, X1): Section0 with the owned interior source cells fused into its epilogue,
 // then the stand-alone scatter for whatever was not fused (halo cells, or everything when fusion is
 // off).  mark(true)/mark(false) are called right before/after a scatter launch (section timers).
@@ -790,6 +803,11 @@ static int plan_step(fdtd_b200_plan *p, int time, bool first_of_run, Mark &&mark
     a.link.epoch = ++p->epoch;
     a.link.wait = first_of_run ? 0 : 1;  // the first step's ghost planes come from the caller's initial state
     a.link.depth = p->t_fuse_used == 2 ? 4 : 2;  // a two-step pass may follow: it reads 4 ghost planes of u[t2]
+    // per-tile flags are valid when the previous launch of this run (on every slab: same schedule) used the same kernel,
+    // hence the same tile grid
+    a.link.tile_mode = (linked && p->opt_tile_flags && !first_of_run && p->last_kind == 1 && p->kernel_used == 2 &&
+                        tile_count_tma(p) <= kMaxFlagTiles) ? 1 : 0;
+    p->last_kind = p->kernel_used == 2 ? 1 : 0;
     int rc;
     if (p->kernel_used == 2)
         rc = launch_stencil_tma(p->tma, a, p->opt_exact != 0, p->stream);
@@ -844,6 +862,12 @@ static int plan_pass2(fdtd_b200_plan *p, int time, bool first_of_run)
     a.link.epoch = ++p->epoch;
     a.link.wait = first_of_run ? 0 : 1;
     a.link.depth = 4;
+    {
+        const bool linked = p->link.peer_u[0] || p->link.peer_u[1];
+        const int tiles = ((p->g.Y1 - p->g.Y0 + p->tb2.ty - 1) / p->tb2.ty) * ((p->g.Z1 - p->g.Z0 + p->tb2.tz - 1) / p->tb2.tz);
+        a.link.tile_mode = (linked && p->opt_tile_flags && !first_of_run && p->last_kind == 2 && tiles <= kMaxFlagTiles) ? 1 : 0;
+        p->last_kind = 2;
+    }
     int rc = p->use_tc2 ? launch_stencil_tc2(p->tc2, a, p->opt_exact != 0, p->stream)
                         : launch_stencil_tb2(p->tb2, a, p->opt_exact != 0, p->stream);
     if (rc) return rc;
@@ -931,6 +955,7 @@ int fdtd::plan_prepare(fdtd_b200_plan *p)
     FDTD_CHECK(cudaSetDevice(p->dev));
     p->last_launches = 0;
     p->last_kernel_seconds = 0.0;
+    p->last_kind = 0;
     const bool can_tma = p->shape.space_order == 4 && tma_supported(p->g);
     int want = p->opt_kernel;
     if (p->shape.space_order != 4) {  // orders 6..12: the one-point-per-thread kernel with R neighbour pairs per axis

@@ -97,6 +97,9 @@ struct fdtd_b200_plan {
     fdtd::SlabLink link{};           // peers (null = physical boundary)
     void *ipc_base[2] = {nullptr, nullptr};  // mappings opened with cudaIpcOpenMemHandle
     int epoch = 0;                   // step sequence number, identical on every slab
+    size_t tile_flags_offset = 0;    // byte offset of the per-tile flag arrays [2][kMaxFlagTiles] inside the u allocation
+    int last_kind = 0;               // kernel of the previous launch of this run: 0 none, 1 one-step streaming, 2 two-step
+    int opt_tile_flags = 1;          // 0: always the whole-boundary flags (FDTD_B200_TILE_FLAGS)
 
     // statistics of the last run
     long last_launches = 0;

@@ -12,6 +12,7 @@ struct SlabBlob {                  // FDTD_B200_IPC_BYTES = 160
     cudaIpcMemHandle_t handle;     // 64 bytes
     long long lvl;
     unsigned long long flags_offset;
+    unsigned long long tile_flags_offset;
     int nxp, nyp, nzp, X0, X1, dev;
     int magic;
 };
@@ -28,6 +29,8 @@ int link_to(fdtd_b200_plan *p, int side, float *peer_u, const SlabBlob &b)
     p->link.peer_lvl[side] = b.lvl;
     p->link.peer_edge[side] = side == 0 ? b.X1 : b.X0;
     p->link.peer_flag[side] = peer_flags + (side == 0 ? 1 : 0);
+    // the neighbour sees this slab on ITS side 1 - side: that is the array this slab raises
+    p->link.peer_tile[side] = reinterpret_cast<int *>(reinterpret_cast<char *>(peer_u) + b.tile_flags_offset) + (side == 0 ? fdtd::kMaxFlagTiles : 0);
     return 0;
 }
 
@@ -36,6 +39,7 @@ void fill_blob(fdtd_b200_plan *p, SlabBlob &b)
     memset(&b, 0, sizeof(b));
     b.lvl = p->g.lvl;
     b.flags_offset = p->flags_offset;
+    b.tile_flags_offset = p->tile_flags_offset;
     b.nxp = p->g.nxp;
     b.nyp = p->g.nyp;
     b.nzp = p->g.nzp;

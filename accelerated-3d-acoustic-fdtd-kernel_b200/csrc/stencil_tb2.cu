@@ -131,10 +131,15 @@ __global__ void __launch_bounds__(Tb2Shape<ER, EC, RY>::NT, 1) stencil_tb2_kerne
     if (threadIdx.x >= T::NC) {
         // ------------------------------------------------------------------ producer (one thread)
         // stage s: u^n plane Xa-4+s; for s >= 4 also u^{n-1} and m plane Xa-6+s (= step-1 plane of iteration s-4)
+        const bool tiled = lk.tile_mode && lk.wait;  // per-tile flags: see stencil_tma.cu
+        if (tiled) {
+            if (lk.peer_u[0] && Xa - 4 < g.X0) wait_tiles(lk.my_tile[0], ty, tz, a.tiles_y, a.tiles_z, lk.epoch - 1, lk.err);
+            if (lk.peer_u[1] && Xb + 4 > g.X1) wait_tiles(lk.my_tile[1], ty, tz, a.tiles_y, a.tiles_z, lk.epoch - 1, lk.err);
+        }
         if (threadIdx.x == T::NC) {
             const int nst = nit + 4;
             int us = 0, ps = 0, ms = 0;
-            bool waited[2] = {!(lk.wait && lk.peer_u[0]), !(lk.wait && lk.peer_u[1])};
+            bool waited[2] = {tiled || !(lk.wait && lk.peer_u[0]), tiled || !(lk.wait && lk.peer_u[1])};
             for (int s = 0; s < nst; ++s) {
                 const int Xp = Xa - 4 + s;  // ghost planes (outside [X0, X1)) are written by the neighbours' previous pass
                 const int side = Xp < g.X0 ? 0 : (Xp >= g.X1 ? 1 : -1);
@@ -328,6 +333,7 @@ __global__ void __launch_bounds__(Tb2Shape<ER, EC, RY>::NT, 1) stencil_tb2_kerne
 #pragma unroll
             for (int side = 0; side < 2; ++side) {
                 if (!(side == 0 ? cta_lo : cta_hi)) continue;
+                raise_flag(lk.peer_tile[side] + blockIdx.x, lk.epoch);  // this tile's boundary is done
                 const int done = atomicAdd(lk.counter + side, 1);
                 if (done == lk.expect[side] - 1) {
                     atomicExch(lk.counter + side, 0);
@@ -484,8 +490,17 @@ int launch_stencil_tb2(const Tb2Plan &p, const Tb2Step &a, bool exact, cudaStrea
     const bool linked = a.link.peer_u[0] != nullptr || a.link.peer_u[1] != nullptr;
     if (linked) {  // short boundary chunks hold the 4 planes a neighbour needs; the usual chunks lie in between
         if (nx < 4 * kSlabEdgePlanes) return (int)cudaErrorInvalidValue;
-        args.edge = slab_edge_planes(nx, p.xchunk, args.tiles_z * args.tiles_y, 0);
-        nchunks = 2 + (nx - 2 * args.edge + p.xchunk - 1) / p.xchunk;
+        if (a.link.tile_mode) {
+            // per-tile flags: the usual chunks, but exactly ONE chunk per side may hold boundary planes (>= 4 planes each)
+            while (nchunks > 1 && (args.xchunk < 4 || nx - (nchunks - 1) * args.xchunk < 4)) {
+                --nchunks;
+                args.xchunk = (nx + nchunks - 1) / nchunks;
+            }
+            nchunks = (nx + args.xchunk - 1) / args.xchunk;
+        } else {
+            args.edge = slab_edge_planes(nx, p.xchunk, args.tiles_z * args.tiles_y, 0);
+            nchunks = 2 + (nx - 2 * args.edge + p.xchunk - 1) / p.xchunk;
+        }
         args.s.link.expect[0] = args.s.link.expect[1] = args.tiles_z * args.tiles_y;
     }
     dim3 grid(args.tiles_z * args.tiles_y, nchunks, 1);

@@ -103,6 +103,8 @@ __global__ void __launch_bounds__(TileShape<TY, TZ, RY, NS>::NT, MINB)
     }
     const int np = Xb - Xa;         // output planes of this CTA (>= 1 by construction)
     const SlabLink &lk = a.s.link;
+    // the chunk with the slab's UPPER boundary streams downwards: its boundary planes leave first (see stencil_tb2.cu)
+    const bool rev = lk.peer_u[1] != nullptr && nch > 1 && chunk == nch - 1;
     const int Yt = g.Y0 + ty * TY;  // padded origin of the tile
     const int Zt = g.Z0 + tz * TZ;
 
@@ -117,12 +119,20 @@ __global__ void __launch_bounds__(TileShape<TY, TZ, RY, NS>::NT, MINB)
 
     if (threadIdx.x >= T::NC) {
         // ------------------------------------------------------------------ producer (one thread)
+        // per-tile flags: the whole producer warp polls the 3 x 3 tiles around its own on the sides whose ghost planes
+        // this chunk reads (and whose neighbour it will write to: same tiles, same condition)
+        const bool tiled = lk.tile_mode && lk.wait;
+        if (tiled) {
+            if (lk.peer_u[0] && Xa - 2 < g.X0) wait_tiles(lk.my_tile[0], ty, tz, a.tiles_y, a.tiles_z, lk.epoch - 1, lk.err);
+            if (lk.peer_u[1] && Xb + 2 > g.X1) wait_tiles(lk.my_tile[1], ty, tz, a.tiles_y, a.tiles_z, lk.epoch - 1, lk.err);
+        }
         if (threadIdx.x == T::NC) {
             const int nst = np + 4;
             int slot = 0, use = 0, cslot = 0;
-            bool waited[2] = {!(lk.wait && lk.peer_u[0]), !(lk.wait && lk.peer_u[1])};
+            bool waited[2] = {tiled || !(lk.wait && lk.peer_u[0]), tiled || !(lk.wait && lk.peer_u[1])};
             for (int s = 0; s < nst; ++s) {
-                const int Xp = Xa - 2 + s;  // u[t0] plane of this stage: a ghost plane outside [X0, X1)
+                const int Xp = rev ? Xb + 1 - s : Xa - 2 + s;  // u[t0] plane of this stage: a ghost plane outside [X0, X1)
+                const int Xc = rev ? Xb + 3 - s : Xa + s - 4;  // u[t1] / m plane of this stage (output plane of iteration s-4)
                 const int side = Xp < g.X0 ? 0 : (Xp >= g.X1 ? 1 : -1);
                 if (side >= 0 && !waited[side]) {
                     wait_flag(lk.my_flag[side], lk.epoch - 1, lk.err);
@@ -132,10 +142,10 @@ __global__ void __launch_bounds__(TileShape<TY, TZ, RY, NS>::NT, MINB)
                 const uint32_t bar = full0 + 8 * slot;
                 const bool ctr = s >= 4;
                 mbar_expect_tx(bar, T::HBYTES + (ctr ? 2 * T::CBYTES : 0));
-                tma_load_4d(smem_u32(sH) + slot * T::HSLOT, &a.map_halo, bar, Zt - 4, Yt - 2, Xa - 2 + s, a.s.t0);
+                tma_load_4d(smem_u32(sH) + slot * T::HSLOT, &a.map_halo, bar, Zt - 4, Yt - 2, Xp, a.s.t0);
                 if (ctr) {
-                    tma_load_4d(smem_u32(sU1) + cslot * T::CBYTES, &a.map_ctr, bar, Zt, Yt, Xa + s - 4, a.s.t1);
-                    tma_load_3d(smem_u32(sM) + cslot * T::CBYTES, &a.map_m, bar, Zt, Yt, Xa + s - 4);
+                    tma_load_4d(smem_u32(sU1) + cslot * T::CBYTES, &a.map_ctr, bar, Zt, Yt, Xc, a.s.t1);
+                    tma_load_3d(smem_u32(sM) + cslot * T::CBYTES, &a.map_m, bar, Zt, Yt, Xc);
                     if (++cslot == S1) cslot = 0;
                 }
                 if (++slot == S0) {
@@ -183,8 +193,9 @@ __global__ void __launch_bounds__(TileShape<TY, TZ, RY, NS>::NT, MINB)
     const long long row0 = (long long)Y * g.nzp + Z;
 
     int ms = 0;  // centre-ring slot j % S1
-    float *__restrict__ out = a.s.u + (long long)a.s.t2 * g.lvl + ((long long)Xa * g.nyp + Y) * g.nzp + Z;
+    float *__restrict__ out = a.s.u + (long long)a.s.t2 * g.lvl + ((long long)(rev ? Xb - 1 : Xa) * g.nyp + Y) * g.nzp + Z;
     const long long plane = (long long)g.nyp * g.nzp;
+    const long long out_step = rev ? -plane : plane;
 
     for (int j0 = 0; j0 < np; j0 += S0) {
         const uint32_t par = (uint32_t)(j0 / S0) & 1u;
@@ -227,7 +238,7 @@ __global__ void __launch_bounds__(TileShape<TY, TZ, RY, NS>::NT, MINB)
             }
 
             if (chunk_has_src) {  // fused Section1: rare path, only chunks that contain a source cell
-                const int X = Xa + j;
+                const int X = rev ? Xb - 1 - j : Xa + j;
                 const int c0 = sv.plane_off[X], c1 = sv.plane_off[X + 1];
                 for (int i = c0; i < c1; ++i) {
                     const SourceCell cell = sv.cells[i];
@@ -255,9 +266,9 @@ __global__ void __launch_bounds__(TileShape<TY, TZ, RY, NS>::NT, MINB)
 #pragma unroll
             for (int r = 0; r < RY; ++r)
                 if (z_ok && Y + r < g.Y1) *reinterpret_cast<float4 *>(out + (long long)r * g.nzp) = o[r];
-            out += plane;
+            out += out_step;
             if (cta_lo || cta_hi) {
-                const int X = Xa + j;
+                const int X = rev ? Xb - 1 - j : Xa + j;
                 if (cta_lo && X < g.X0 + lk.depth) {
                     float *dst = lk.peer_u[0] + a.s.t2 * lk.peer_lvl[0] + (long long)(lk.peer_edge[0] + X - g.X0) * plane + row0;
 #pragma unroll
@@ -284,6 +295,7 @@ __global__ void __launch_bounds__(TileShape<TY, TZ, RY, NS>::NT, MINB)
 #pragma unroll
             for (int side = 0; side < 2; ++side) {
                 if (!(side == 0 ? cta_lo : cta_hi)) continue;
+                raise_flag(lk.peer_tile[side] + blockIdx.x, lk.epoch);  // this tile's boundary is done (blockIdx.x = ty*tiles_z + tz)
                 const int done = atomicAdd(lk.counter + side, 1);
                 if (done == lk.expect[side] - 1) {
                     atomicExch(lk.counter + side, 0);
@@ -468,8 +480,18 @@ int launch_stencil_tma(const TmaPlan &p, const StepArgs &a, bool exact, cudaStre
     args.edge = 0;
     int nchunks = (nx + p.xchunk - 1) / p.xchunk;
     const bool linked = a.link.peer_u[0] != nullptr || a.link.peer_u[1] != nullptr;
-    if (linked && nx >= 4 * kSlabEdgePlanes) {  // short boundary chunks + the usual chunks in between
+    if (linked) {
+        // exactly ONE chunk per side may hold boundary planes (its CTA raises the tile's flag when it is done): every
+        // chunk at least 4 planes long, else fewer and longer chunks
+        while (nchunks > 1 && (args.xchunk < 4 || nx - (nchunks - 1) * args.xchunk < 4)) {
+            --nchunks;
+            args.xchunk = (nx + nchunks - 1) / nchunks;
+        }
+        nchunks = (nx + args.xchunk - 1) / args.xchunk;
+    }
+    if (linked && nx >= 4 * kSlabEdgePlanes && !a.link.tile_mode) {  // short boundary chunks + the usual chunks in between
         args.edge = slab_edge_planes(nx, p.xchunk, args.tiles_z * args.tiles_y, 0);
+        args.xchunk = p.xchunk;
         nchunks = 2 + (nx - 2 * args.edge + p.xchunk - 1) / p.xchunk;
     }
     dim3 grid(args.tiles_z * args.tiles_y, nchunks, 1);
@@ -479,9 +501,7 @@ int launch_stencil_tma(const TmaPlan &p, const StepArgs &a, bool exact, cudaStre
     if (args.edge) {
         args.s.link.expect[0] = args.s.link.expect[1] = tiles;
     } else {
-        const int last_len = nx - (nchunks - 1) * p.xchunk;
-        args.s.link.expect[0] = tiles * ((p.xchunk >= 2 || nchunks == 1) ? 1 : 2);
-        args.s.link.expect[1] = tiles * ((last_len >= 2 || nchunks == 1) ? 1 : 2);
+        args.s.link.expect[0] = args.s.link.expect[1] = tiles;  // one chunk per side (see above)
     }
     v.fn<<<grid, v.nt, v.smem, stream>>>(args);
     return (int)cudaGetLastError();

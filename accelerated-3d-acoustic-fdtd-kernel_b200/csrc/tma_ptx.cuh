@@ -71,6 +71,18 @@ __device__ __forceinline__ void wait_flag(const int *flag, int want, int *err)
     }
     asm volatile("fence.proxy.async;" ::: "memory");  // the ghost planes are read by TMA (async proxy)
 }
+// The same for the 3 x 3 tiles around (ty, tz) of a per-tile flag array, polled by lanes 0..8 of ONE converged warp
+// (indices clamped at the edges of the tile grid); every lane of the warp may rely on the neighbours' data afterwards.
+__device__ __forceinline__ void wait_tiles(const int *flags, int ty, int tz, int tiles_y, int tiles_z, int want, int *err)
+{
+    const int lane = threadIdx.x & 31;
+    if (lane < 9) {
+        const int y = min(max(ty + lane / 3 - 1, 0), tiles_y - 1), z = min(max(tz + lane % 3 - 1, 0), tiles_z - 1);
+        wait_flag(flags + y * tiles_z + z, want, err);
+    }
+    __syncwarp();
+    asm volatile("fence.proxy.async;" ::: "memory");
+}
 __device__ __forceinline__ void raise_flag(int *flag, int value)
 {
     asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(flag), "r"(value) : "memory");

@@ -81,6 +81,12 @@ struct SlabLink {
     int *my_tile[2];         // arrays in this slab's memory raised by the neighbours
     int *peer_tile[2];       // arrays in the neighbours' memory that THIS slab raises
     int tile_mode;           // 1: wait on my_tile[side][3x3 around the tile] >= epoch-1 instead of my_flag[side]
+    // PULL mode (option "halo_pull", off by default): instead of storing its boundary planes into the neighbours' ghost
+    // planes, a slab leaves them where they are and the neighbours' TMA producers read them straight from this slab's
+    // memory through peer tensor maps.  Same flags, no remote stores to wait for -- but the remote loads sit on the
+    // boundary CTAs' critical path, and on 8 GPUs pushing is 2-5 % faster (profiles/r02_slab_protocol_ab_8gpu.txt).
+    int pull;
+    int peer_nxp[2];         // padded planes of the neighbours' arrays (the peer tensor maps' x extent)
 };
 constexpr int kMaxFlagTiles = 16384;  // tiles per side the per-tile flag arrays can hold
 

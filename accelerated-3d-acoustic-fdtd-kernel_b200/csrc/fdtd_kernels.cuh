@@ -43,6 +43,7 @@ struct TmaPlan {         // built once per (arrays, config): tensor maps + launc
     alignas(64) CUtensorMap map_halo;  // u as (z,y,x,t), box (tz+8, ty+4, 1, 1)
     alignas(64) CUtensorMap map_ctr;   // u as (z,y,x,t), box (tz, ty, 1, 1)
     alignas(64) CUtensorMap map_m;     // m as (z,y,x),   box (tz, ty, 1)
+    alignas(64) CUtensorMap map_halo_peer[2];  // the neighbours' u, same box as map_halo (pull mode)
     int ty, tz, rows, stages, xchunk;
     int variant;         // index into the instantiation table
     size_t smem_bytes;
@@ -51,7 +52,7 @@ struct TmaPlan {         // built once per (arrays, config): tensor maps + launc
 // Can the TMA kernel run on this geometry?  (row pitch and z origin 16-byte aligned, nz % 4 == 0)
 bool tma_supported(const Grid &g);
 int tma_plan_build(TmaPlan &p, float *u, const float *m, const Grid &g, const TmaConfig &cfg, bool exact,
-                   int sm_count);
+                   int sm_count, const SlabLink *link = nullptr);
 int launch_stencil_tma(const TmaPlan &p, const StepArgs &a, bool exact, cudaStream_t stream);
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda): fp32, no swizzle, OOB = 0.
@@ -63,6 +64,7 @@ struct Tb2Plan {
     alignas(64) CUtensorMap map_cur;   // u as (z,y,x,level), box (tz+8, ty+8, 1, 1): u^n with the radius-4 halo
     alignas(64) CUtensorMap map_prev;  // u as (z,y,x,level), box (tz+8, ty+4, 1, 1): u^{n-1} on the extended tile
     alignas(64) CUtensorMap map_m;     // m as (z,y,x), box (tz+8, ty+4, 1)
+    alignas(64) CUtensorMap map_cur_peer[2], map_prev_peer[2];  // the neighbours' u, same boxes (pull mode)
     int ty, tz, rows, xchunk, variant;  // output tile, rows per thread, x planes per CTA
     size_t smem_bytes;
     bool valid = false;
@@ -93,7 +95,8 @@ constexpr int kSlabEdgePlanes = 8;     // shortest slab side that can run linked
 // Length of the two boundary chunks of a linked slab of nx planes (they are dispatched first and raise the neighbours'
 // flags): FDTD_B200_SLAB_EDGE overrides; 2*edge == nx means "no chunks in between" (the slabs then run in lock step).
 int slab_edge_planes(int nx, int xchunk, int tiles, int slots);
-int tb2_plan_build(Tb2Plan &p, float *u, const float *m, const Grid &g, const TmaConfig &cfg, bool exact, int sm_count);
+int tb2_plan_build(Tb2Plan &p, float *u, const float *m, const Grid &g, const TmaConfig &cfg, bool exact, int sm_count,
+                   const SlabLink *link = nullptr);
 int launch_stencil_tb2(const Tb2Plan &p, const Tb2Step &a, bool exact, cudaStream_t stream);
 // 1 in *flag (device) unless the shells (every padded cell outside g's box) of levels 0..2 are bit-identical
 int launch_shell_check(float *u, const Grid &g, int *flag, cudaStream_t stream);

@@ -226,6 +226,7 @@ int fdtd::plan_create_internal(const PlanShape &s, fdtd_b200_plan **out, bool ca
     p->tile_flags_offset = p->arena_offset + kArenaBytes;
     p->u_bytes = p->tile_flags_offset + 2 * (size_t)kMaxFlagTiles * sizeof(int);
     p->opt_tile_flags = env_int("FDTD_B200_TILE_FLAGS", 1);
+    p->opt_halo_pull = env_int("FDTD_B200_HALO_PULL", 0);
     p->m_bytes = (size_t)p->g.lvl * sizeof(float);
     const char *nc = getenv("FDTD_B200_NO_CACHE");
     p->cache_buffers = cache_buffers && !(nc && *nc == '1');
@@ -718,6 +719,7 @@ static int *option_slot(fdtd_b200_plan *p, const char *key)
     if (!strcmp(key, "t_fuse_agreed")) return &p->t_fuse_agreed;
     if (!strcmp(key, "cluster")) return &p->opt_cluster;
     if (!strcmp(key, "tile_flags")) return &p->opt_tile_flags;
+    if (!strcmp(key, "halo_pull")) return &p->opt_halo_pull;
     if (!strcmp(key, "stage_planes")) return &p->opt_stage_planes;
     return nullptr;
 }
@@ -977,6 +979,9 @@ int fdtd::plan_prepare(fdtd_b200_plan *p)
     if (want == 2 && !can_tma) return (int)cudaErrorInvalidValue;
     if ((p->link.peer_u[0] || p->link.peer_u[1]) && want != 2) return (int)cudaErrorNotSupported;  // slabs need the streaming kernel
     p->kernel_used = want;
+    // receivers sample the slab's own ghost planes, which only the push protocol keeps current (nrec_total is the same on
+    // every slab, so all slabs decide alike)
+    p->link.pull = (linked && p->opt_halo_pull && p->nrec_total == 0) ? 1 : 0;
     // two time steps per pass: a lone slab decides for itself, linked slabs use the depth they agreed on
     p->t_fuse_used = 1;
     if (want == 2 && p->opt_t_fuse >= 2) {
@@ -993,16 +998,16 @@ int fdtd::plan_prepare(fdtd_b200_plan *p)
             if (rc) return rc;
         }
         if (depth == 2 && !p->use_tc2 && !p->tb2.valid) {
-            int rc = tb2_plan_build(p->tb2, p->d_u, p->d_m, p->g, p->cfg, p->opt_exact != 0, p->sm_count);
+            int rc = tb2_plan_build(p->tb2, p->d_u, p->d_m, p->g, p->cfg, p->opt_exact != 0, p->sm_count, &p->link);
             if (rc) return rc;
         }
         p->t_fuse_used = depth;
     }
     if (want == 2 && !p->tma.valid) {
-        int rc = tma_plan_build(p->tma, p->d_u, p->d_m, p->g, p->cfg, p->opt_exact != 0, p->sm_count);
+        int rc = tma_plan_build(p->tma, p->d_u, p->d_m, p->g, p->cfg, p->opt_exact != 0, p->sm_count, &p->link);
         // with two-step passes the tile options describe that kernel; the one-step kernel (used for the steps
         // that do not pair up) then takes its default tile
-        if (rc && p->t_fuse_used == 2) rc = tma_plan_build(p->tma, p->d_u, p->d_m, p->g, TmaConfig{}, p->opt_exact != 0, p->sm_count);
+        if (rc && p->t_fuse_used == 2) rc = tma_plan_build(p->tma, p->d_u, p->d_m, p->g, TmaConfig{}, p->opt_exact != 0, p->sm_count, &p->link);
         if (rc) return rc;
     }
     if (p->ncells_all > 0 || p->ncells2 > 0) {  // m at every source's base corner (m may have been re-uploaded)

@@ -28,6 +28,8 @@ int link_to(fdtd_b200_plan *p, int side, float *peer_u, const SlabBlob &b)
     p->link.peer_u[side] = peer_u;
     p->link.peer_lvl[side] = b.lvl;
     p->link.peer_edge[side] = side == 0 ? b.X1 : b.X0;
+    p->link.peer_nxp[side] = b.nxp;
+    p->tma.valid = p->tb2.valid = false;  // the plans hold tensor maps of the neighbours' arrays
     p->link.peer_flag[side] = peer_flags + (side == 0 ? 1 : 0);
     // the neighbour sees this slab on ITS side 1 - side: that is the array this slab raises
     p->link.peer_tile[side] = reinterpret_cast<int *>(reinterpret_cast<char *>(peer_u) + b.tile_flags_offset) + (side == 0 ? fdtd::kMaxFlagTiles : 0);

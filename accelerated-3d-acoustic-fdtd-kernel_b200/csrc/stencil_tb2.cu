@@ -33,6 +33,7 @@ struct Tb2Args {
     alignas(64) CUtensorMap map_cur;
     alignas(64) CUtensorMap map_prev;
     alignas(64) CUtensorMap map_m;
+    alignas(64) CUtensorMap map_cur_peer[2], map_prev_peer[2];  // pull mode: the neighbours' u
     Tb2Step s;
     int tiles_z, tiles_y, xchunk;
     int edge;  // > 0: the first and last chunk are `edge` planes long (slabs with neighbours)
@@ -155,9 +156,18 @@ __global__ void __launch_bounds__(Tb2Shape<ER, EC, RY>::NT, 1) stencil_tb2_kerne
                 const uint32_t bar = full0 + 8 * us;
                 const bool ctr = s >= 4;
                 mbar_expect_tx(bar, T::UBYTES + (ctr ? 2 * T::CBYTES : 0));
-                tma_load_4d(smem_u32(sU) + us * T::USLOT, &a.map_cur, bar, Zt - 4, Yt - 4, Xp, a.s.l_cur);
+                if (lk.pull && side >= 0 && lk.peer_u[side])  // a neighbour's plane, read where it lies (same level placement on every slab)
+                    tma_load_4d(smem_u32(sU) + us * T::USLOT, &a.map_cur_peer[side], bar, Zt - 4, Yt - 4,
+                                lk.peer_edge[side] + Xp - (side == 0 ? g.X0 : g.X1), a.s.l_cur);
+                else
+                    tma_load_4d(smem_u32(sU) + us * T::USLOT, &a.map_cur, bar, Zt - 4, Yt - 4, Xp, a.s.l_cur);
                 if (ctr) {
-                    tma_load_4d(smem_u32(sP) + ps * T::CSLOT, &a.map_prev, bar, Zt - 4, Yt - 2, Xp - 2, a.s.l_prev);
+                    const int Xq = Xp - 2, sq = Xq < g.X0 ? 0 : (Xq >= g.X1 ? 1 : -1);
+                    if (lk.pull && sq >= 0 && lk.peer_u[sq])
+                        tma_load_4d(smem_u32(sP) + ps * T::CSLOT, &a.map_prev_peer[sq], bar, Zt - 4, Yt - 2,
+                                    lk.peer_edge[sq] + Xq - (sq == 0 ? g.X0 : g.X1), a.s.l_prev);
+                    else
+                        tma_load_4d(smem_u32(sP) + ps * T::CSLOT, &a.map_prev, bar, Zt - 4, Yt - 2, Xp - 2, a.s.l_prev);
                     tma_load_3d(smem_u32(sM) + ms * T::CSLOT, &a.map_m, bar, Zt - 4, Yt - 2, Xp - 2);
                     if (++ps == SP) ps = 0;
                     if (++ms == SM) ms = 0;
@@ -203,6 +213,7 @@ __global__ void __launch_bounds__(Tb2Shape<ER, EC, RY>::NT, 1) stencil_tb2_kerne
     // planes of u^{n+1} and the four outermost planes of u^{n+2}
     const bool cta_lo = lk.peer_u[0] != nullptr && Xa < g.X0 + 4;
     const bool cta_hi = lk.peer_u[1] != nullptr && Xb > g.X1 - 4;
+    const bool push_lo = cta_lo && !lk.pull, push_hi = cta_hi && !lk.pull;  // pull mode: the neighbours read our planes in place
 
     // register queues: qU[s % 5][r] = own rows of u^n, stage s (plane Xa-4+s); qR[i % 5][r] = own step-1 results of
     // iteration i (plane Xa-2+i).  The loop is unrolled by 5 so every index is a compile-time constant.
@@ -265,9 +276,9 @@ __global__ void __launch_bounds__(Tb2Shape<ER, EC, RY>::NT, 1) stencil_tb2_kerne
                     if (inb[r]) res[r] = v;
                     if (core[r] && P1 >= Xa && P1 < Xb) {
                         *reinterpret_cast<float4 *>(out1 + (long long)P1 * plane + r * g.nzp) = v;
-                        if (cta_lo && P1 < g.X0 + 2)
+                        if (push_lo && P1 < g.X0 + 2)
                             *reinterpret_cast<float4 *>(lk.peer_u[0] + a.s.l_n1 * lk.peer_lvl[0] + (long long)(lk.peer_edge[0] + P1 - g.X0) * plane + row0 + r * g.nzp) = v;
-                        if (cta_hi && P1 >= g.X1 - 2)
+                        if (push_hi && P1 >= g.X1 - 2)
                             *reinterpret_cast<float4 *>(lk.peer_u[1] + a.s.l_n1 * lk.peer_lvl[1] + (long long)(lk.peer_edge[1] + P1 - g.X1) * plane + row0 + r * g.nzp) = v;
                     }
                 }
@@ -300,9 +311,9 @@ __global__ void __launch_bounds__(Tb2Shape<ER, EC, RY>::NT, 1) stencil_tb2_kerne
                         if (chunk_has_src) inject_plane(o, X, Y + r, Z, sv2);  // source cells of step n+1
                         if (core[r]) {
                             *reinterpret_cast<float4 *>(out2 + (long long)X * plane + r * g.nzp) = o;
-                            if (cta_lo && X < g.X0 + 4)
+                            if (push_lo && X < g.X0 + 4)
                                 *reinterpret_cast<float4 *>(lk.peer_u[0] + a.s.l_n2 * lk.peer_lvl[0] + (long long)(lk.peer_edge[0] + X - g.X0) * plane + row0 + r * g.nzp) = o;
-                            if (cta_hi && X >= g.X1 - 4)
+                            if (push_hi && X >= g.X1 - 4)
                                 *reinterpret_cast<float4 *>(lk.peer_u[1] + a.s.l_n2 * lk.peer_lvl[1] + (long long)(lk.peer_edge[1] + X - g.X1) * plane + row0 + r * g.nzp) = o;
                         }
                     }
@@ -333,12 +344,12 @@ __global__ void __launch_bounds__(Tb2Shape<ER, EC, RY>::NT, 1) stencil_tb2_kerne
 #pragma unroll
             for (int side = 0; side < 2; ++side) {
                 if (!(side == 0 ? cta_lo : cta_hi)) continue;
-                raise_flag(lk.peer_tile[side] + blockIdx.x, lk.epoch);  // this tile's boundary is done
+                raise_flag_fenced(lk.peer_tile[side] + blockIdx.x, lk.epoch);  // this tile's boundary is done
                 const int done = atomicAdd(lk.counter + side, 1);
                 if (done == lk.expect[side] - 1) {
                     atomicExch(lk.counter + side, 0);
                     __threadfence_system();
-                    raise_flag(lk.peer_flag[side], lk.epoch);
+                    raise_flag_fenced(lk.peer_flag[side], lk.epoch);
                 }
             }
         }
@@ -415,7 +426,8 @@ static const Tb2Variant g_tb2[] = {
 };
 static const int g_ntb2 = (int)(sizeof(g_tb2) / sizeof(g_tb2[0]));
 
-int tb2_plan_build(Tb2Plan &p, float *u, const float *m, const Grid &g, const TmaConfig &cfg, bool exact, int sm_count)
+int tb2_plan_build(Tb2Plan &p, float *u, const float *m, const Grid &g, const TmaConfig &cfg, bool exact, int sm_count,
+                   const SlabLink *link)
 {
     p.valid = false;
     if (!tma_supported(g)) return (int)cudaErrorInvalidValue;
@@ -440,6 +452,14 @@ int tb2_plan_build(Tb2Plan &p, float *u, const float *m, const Grid &g, const Tm
     if ((rc = encode_tensor_map(&p.map_cur, u, 4, dims_u, box_u))) return rc;
     if ((rc = encode_tensor_map(&p.map_prev, u, 4, dims_u, box_c))) return rc;
     if ((rc = encode_tensor_map(&p.map_m, m, 3, dims_u, box_c))) return rc;
+    for (int side = 0; side < 2; ++side) {
+        p.map_cur_peer[side] = p.map_cur;
+        p.map_prev_peer[side] = p.map_prev;
+        if (!link || !link->peer_u[side]) continue;
+        cuuint64_t dims_p[4] = {(cuuint64_t)g.nzp, (cuuint64_t)g.nyp, (cuuint64_t)link->peer_nxp[side], (cuuint64_t)FDTD_LEVELS};
+        if ((rc = encode_tensor_map(&p.map_cur_peer[side], link->peer_u[side], 4, dims_p, box_u))) return rc;
+        if ((rc = encode_tensor_map(&p.map_prev_peer[side], link->peer_u[side], 4, dims_p, box_c))) return rc;
+    }
     cudaError_t e = cudaFuncSetAttribute((const void *)v.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v.smem);
     if (e != cudaSuccess) return (int)e;
 
@@ -481,6 +501,10 @@ int launch_stencil_tb2(const Tb2Plan &p, const Tb2Step &a, bool exact, cudaStrea
     args.map_cur = p.map_cur;
     args.map_prev = p.map_prev;
     args.map_m = p.map_m;
+    for (int side = 0; side < 2; ++side) {
+        args.map_cur_peer[side] = p.map_cur_peer[side];
+        args.map_prev_peer[side] = p.map_prev_peer[side];
+    }
     args.s = a;
     args.tiles_z = (nz + p.tz - 1) / p.tz;
     args.tiles_y = (ny + p.ty - 1) / p.ty;

@@ -34,6 +34,7 @@ struct TmaArgs {
     alignas(64) CUtensorMap map_halo;
     alignas(64) CUtensorMap map_ctr;
     alignas(64) CUtensorMap map_m;
+    alignas(64) CUtensorMap map_halo_peer[2];  // pull mode: the neighbours' u
     StepArgs s;
     int tiles_z, tiles_y, xchunk;
     int edge;  // > 0: the first and last chunk are only `edge` planes long (slabs with neighbours)
@@ -142,7 +143,11 @@ __global__ void __launch_bounds__(TileShape<TY, TZ, RY, NS>::NT, MINB)
                 const uint32_t bar = full0 + 8 * slot;
                 const bool ctr = s >= 4;
                 mbar_expect_tx(bar, T::HBYTES + (ctr ? 2 * T::CBYTES : 0));
-                tma_load_4d(smem_u32(sH) + slot * T::HSLOT, &a.map_halo, bar, Zt - 4, Yt - 2, Xp, a.s.t0);
+                if (lk.pull && side >= 0 && lk.peer_u[side])  // a neighbour's plane, read where it lies (same level placement on every slab)
+                    tma_load_4d(smem_u32(sH) + slot * T::HSLOT, &a.map_halo_peer[side], bar, Zt - 4, Yt - 2,
+                                lk.peer_edge[side] + Xp - (side == 0 ? g.X0 : g.X1), a.s.t0);
+                else
+                    tma_load_4d(smem_u32(sH) + slot * T::HSLOT, &a.map_halo, bar, Zt - 4, Yt - 2, Xp, a.s.t0);
                 if (ctr) {
                     tma_load_4d(smem_u32(sU1) + cslot * T::CBYTES, &a.map_ctr, bar, Zt, Yt, Xc, a.s.t1);
                     tma_load_3d(smem_u32(sM) + cslot * T::CBYTES, &a.map_m, bar, Zt, Yt, Xc);
@@ -267,7 +272,7 @@ __global__ void __launch_bounds__(TileShape<TY, TZ, RY, NS>::NT, MINB)
             for (int r = 0; r < RY; ++r)
                 if (z_ok && Y + r < g.Y1) *reinterpret_cast<float4 *>(out + (long long)r * g.nzp) = o[r];
             out += out_step;
-            if (cta_lo || cta_hi) {
+            if ((cta_lo || cta_hi) && !lk.pull) {
                 const int X = rev ? Xb - 1 - j : Xa + j;
                 if (cta_lo && X < g.X0 + lk.depth) {
                     float *dst = lk.peer_u[0] + a.s.t2 * lk.peer_lvl[0] + (long long)(lk.peer_edge[0] + X - g.X0) * plane + row0;
@@ -295,12 +300,12 @@ __global__ void __launch_bounds__(TileShape<TY, TZ, RY, NS>::NT, MINB)
 #pragma unroll
             for (int side = 0; side < 2; ++side) {
                 if (!(side == 0 ? cta_lo : cta_hi)) continue;
-                raise_flag(lk.peer_tile[side] + blockIdx.x, lk.epoch);  // this tile's boundary is done (blockIdx.x = ty*tiles_z + tz)
+                raise_flag_fenced(lk.peer_tile[side] + blockIdx.x, lk.epoch);  // this tile's boundary is done (blockIdx.x = ty*tiles_z + tz)
                 const int done = atomicAdd(lk.counter + side, 1);
                 if (done == lk.expect[side] - 1) {
                     atomicExch(lk.counter + side, 0);
                     __threadfence_system();
-                    raise_flag(lk.peer_flag[side], lk.epoch);
+                    raise_flag_fenced(lk.peer_flag[side], lk.epoch);
                 }
             }
         }
@@ -388,7 +393,7 @@ int encode_tensor_map(CUtensorMap *map, const float *base, int rank, const cuuin
 }
 
 int tma_plan_build(TmaPlan &p, float *u, const float *m, const Grid &g, const TmaConfig &cfg, bool exact,
-                   int sm_count)
+                   int sm_count, const SlabLink *link)
 {
     p.valid = false;
     if (!tma_supported(g)) return (int)cudaErrorInvalidValue;
@@ -418,6 +423,12 @@ int tma_plan_build(TmaPlan &p, float *u, const float *m, const Grid &g, const Tm
     if ((rc = encode_tensor_map(&p.map_halo, u, 4, dims_u, box_h))) return rc;
     if ((rc = encode_tensor_map(&p.map_ctr, u, 4, dims_u, box_c))) return rc;
     if ((rc = encode_tensor_map(&p.map_m, m, 3, dims_u, box_c))) return rc;
+    for (int side = 0; side < 2; ++side) {
+        p.map_halo_peer[side] = p.map_halo;
+        if (!link || !link->peer_u[side]) continue;
+        cuuint64_t dims_p[4] = {(cuuint64_t)g.nzp, (cuuint64_t)g.nyp, (cuuint64_t)link->peer_nxp[side], (cuuint64_t)FDTD_LEVELS};
+        if ((rc = encode_tensor_map(&p.map_halo_peer[side], link->peer_u[side], 4, dims_p, box_h))) return rc;
+    }
 
     cudaError_t e = cudaFuncSetAttribute((const void *)v.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v.smem);
     if (e != cudaSuccess) return (int)e;
@@ -473,6 +484,8 @@ int launch_stencil_tma(const TmaPlan &p, const StepArgs &a, bool exact, cudaStre
     args.map_halo = p.map_halo;
     args.map_ctr = p.map_ctr;
     args.map_m = p.map_m;
+    args.map_halo_peer[0] = p.map_halo_peer[0];
+    args.map_halo_peer[1] = p.map_halo_peer[1];
     args.s = a;
     args.tiles_z = (nz + p.tz - 1) / p.tz;
     args.tiles_y = (ny + p.ty - 1) / p.ty;

@@ -441,8 +441,17 @@ extern "C" int fdtd_b200_plan_run_staged(fdtd_b200_plan *p, float *h_u, const fl
     };
 
     // one-step launch plan for a block: the streaming kernel with one x chunk per tile
+    // ... unless the block's tiles alone cannot fill the machine (256^3 with 8 x 64 tiles: 128 CTAs on 148 SMs, each
+    // streaming all B planes -- latency-bound, 30 us for 5 us of work): then the block is cut into x chunks of >= 8 planes
+    // until there are ~4 CTAs per SM
     TmaPlan tma_block = p->tma;
     tma_block.xchunk = B;
+    if (p->kernel_used == 2) {
+        const int tiles = ((g.Y1 - g.Y0 + p->tma.ty - 1) / p->tma.ty) * ((g.Z1 - g.Z0 + p->tma.tz - 1) / p->tma.tz);
+        int nch = (4 * p->sm_count + tiles - 1) / tiles;
+        nch = std::max(1, std::min(nch, B / 8));
+        tma_block.xchunk = (B + nch - 1) / nch;
+    }
     const int first_timed = time_m + FDTD_WARMUP_STEPS;
     // skewed blocks: b = 0 .. nblocks-1 until the last step's window has passed X1
     const int nblocks = (nx + 2 * (T - 1) + B - 1) / B;

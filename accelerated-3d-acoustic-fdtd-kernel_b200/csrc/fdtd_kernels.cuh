@@ -38,6 +38,7 @@ struct TmaConfig {
     int rows = 0;        // y rows per consumer thread (1, 2 or 4); 0 = auto
     int stages = 0;      // halo-plane ring depth (5 or 10); 0 = 5
     int xchunk = 0;      // x planes per CTA; 0 = auto
+    int lean = 1;        // two-step passes: 1 = stencil_tb2l.cu (lean inner loop), 0 = stencil_tb2.cu
 };
 struct TmaPlan {         // built once per (arrays, config): tensor maps + launch shape
     alignas(64) CUtensorMap map_halo;  // u as (z,y,x,t), box (tz+8, ty+4, 1, 1)
@@ -66,6 +67,7 @@ struct Tb2Plan {
     alignas(64) CUtensorMap map_m;     // m as (z,y,x), box (tz+8, ty+4, 1)
     alignas(64) CUtensorMap map_cur_peer[2], map_prev_peer[2];  // the neighbours' u, same boxes (pull mode)
     int ty, tz, rows, xchunk, variant;  // output tile, rows per thread, x planes per CTA
+    bool lean = false;                  // variant indexes stencil_tb2l.cu's table
     size_t smem_bytes;
     bool valid = false;
 };

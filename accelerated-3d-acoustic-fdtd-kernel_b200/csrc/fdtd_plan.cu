@@ -218,6 +218,7 @@ int fdtd::plan_create_internal(const PlanShape &s, fdtd_b200_plan **out, bool ca
     p->cfg.xchunk = env_int("FDTD_B200_XCHUNK", 0);
     p->opt_t_fuse = env_int("FDTD_B200_T_FUSE", g_t_fuse);
     p->opt_cluster = env_int("FDTD_B200_CLUSTER", 0);
+    p->cfg.lean = env_int("FDTD_B200_TB2_LEAN", 1);
     p->opt_stage_planes = env_int("FDTD_B200_STAGE_PLANES", -1);
 
     cudaError_t e = cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking);
@@ -718,6 +719,7 @@ static int *option_slot(fdtd_b200_plan *p, const char *key)
     if (!strcmp(key, "xchunk")) return &p->cfg.xchunk;
     if (!strcmp(key, "t_fuse_agreed")) return &p->t_fuse_agreed;
     if (!strcmp(key, "cluster")) return &p->opt_cluster;
+    if (!strcmp(key, "tb2_lean")) return &p->cfg.lean;
     if (!strcmp(key, "tile_flags")) return &p->opt_tile_flags;
     if (!strcmp(key, "halo_pull")) return &p->opt_halo_pull;
     if (!strcmp(key, "stage_planes")) return &p->opt_stage_planes;

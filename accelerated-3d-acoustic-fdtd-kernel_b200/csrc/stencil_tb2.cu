@@ -24,20 +24,11 @@
 #include "fdtd_arith.cuh"
 #include "fdtd_kernels.cuh"
 #include "tma_ptx.cuh"
+#include "stencil_tb2.cuh"
 
 #include <math.h>
 
 namespace fdtd {
-
-struct Tb2Args {
-    alignas(64) CUtensorMap map_cur;
-    alignas(64) CUtensorMap map_prev;
-    alignas(64) CUtensorMap map_m;
-    alignas(64) CUtensorMap map_cur_peer[2], map_prev_peer[2];  // pull mode: the neighbours' u
-    Tb2Step s;
-    int tiles_z, tiles_y, xchunk;
-    int edge;  // > 0: the first and last chunk are `edge` planes long (slabs with neighbours)
-};
 
 template <int ER, int EC, int RY>
 struct Tb2Shape {
@@ -59,24 +50,6 @@ struct Tb2Shape {
     static_assert(NT <= 1024, "too many threads");
     static_assert(SMEM <= 232448, "shared memory of one CTA exceeds 227 KB");
 };
-
-// Source cells of one plane that fall into this thread's float4: add their contributions in p_src order.
-__device__ __forceinline__ void inject_plane(float4 &r, int X, int Y, int Z, const SourceView &sv)
-{
-    const int c0 = sv.plane_off[X], c1 = sv.plane_off[X + 1];
-    for (int q = c0; q < c1; ++q) {
-        const SourceCell cell = sv.cells[q];
-        const int dzc = cell.Z - Z;
-        if (cell.Y == Y && dzc >= 0 && dzc < 4) {
-            float v = dzc == 0 ? r.x : dzc == 1 ? r.y : dzc == 2 ? r.z : r.w;
-            v = apply_cell(v, cell, sv);
-            r.x = dzc == 0 ? v : r.x;
-            r.y = dzc == 1 ? v : r.y;
-            r.z = dzc == 2 ? v : r.z;
-            r.w = dzc == 3 ? v : r.w;
-        }
-    }
-}
 
 template <int ER, int EC, int RY, bool EXACT>
 __global__ void __launch_bounds__(Tb2Shape<ER, EC, RY>::NT, 1) stencil_tb2_kernel(const __grid_constant__ Tb2Args a)
@@ -402,14 +375,6 @@ int launch_shell_copy(float *u, const Grid &g, int from, int to, cudaStream_t st
 }
 
 // ---------------------------------------------------------------------------- host side
-typedef void (*Tb2KernelFn)(const Tb2Args);
-struct Tb2Variant {
-    int er, ec, rows;
-    bool exact;
-    Tb2KernelFn fn;
-    int nt;
-    size_t smem;
-};
 #define FDTD_TB2_1(ER_, EC_, RY_, EX_) \
     {ER_, EC_, RY_, EX_, stencil_tb2_kernel<ER_, EC_, RY_, EX_>, Tb2Shape<ER_, EC_, RY_>::NT, (size_t)Tb2Shape<ER_, EC_, RY_>::SMEM}
 #define FDTD_TB2(ER_, EC_, RY_) FDTD_TB2_1(ER_, EC_, RY_, false), FDTD_TB2_1(ER_, EC_, RY_, true)
@@ -436,13 +401,18 @@ int tb2_plan_build(Tb2Plan &p, float *u, const float *m, const Grid &g, const Tm
     // TMA box), else 32 x 64
     int want_ty = cfg.ty, want_tz = cfg.tz;
     if (want_ty <= 0 && want_tz <= 0 && ny % 16 == 0 && nz % 128 == 0) want_ty = 16, want_tz = 128;
+    // the lean kernel (stencil_tb2l.cu) has one row per thread; two rows per thread exist in the first kernel only
+    const bool lean = cfg.lean != 0 && cfg.rows != 2;
+    int ntab = g_ntb2;
+    const Tb2Variant *tab = g_tb2;
+    if (lean) tab = tb2l_variants(&ntab);
     int vi = -1;
-    for (int i = 0; i < g_ntb2 && vi < 0; ++i)
-        if (g_tb2[i].exact == exact && (want_ty <= 0 || g_tb2[i].er - 4 == want_ty) && (want_tz <= 0 || 4 * g_tb2[i].ec - 8 == want_tz) &&
-            (cfg.rows <= 0 || g_tb2[i].rows == cfg.rows))
+    for (int i = 0; i < ntab && vi < 0; ++i)
+        if (tab[i].exact == exact && (want_ty <= 0 || tab[i].er - 4 == want_ty) && (want_tz <= 0 || 4 * tab[i].ec - 8 == want_tz) &&
+            (cfg.rows <= 0 ? tab[i].rows <= 2 : tab[i].rows == cfg.rows))
             vi = i;
     if (vi < 0) return (int)cudaErrorInvalidValue;
-    const Tb2Variant &v = g_tb2[vi];
+    const Tb2Variant &v = tab[vi];
     const int ty = v.er - 4, tz = 4 * v.ec - 8;
 
     cuuint64_t dims_u[4] = {(cuuint64_t)g.nzp, (cuuint64_t)g.nyp, (cuuint64_t)g.nxp, (cuuint64_t)FDTD_LEVELS};
@@ -485,6 +455,7 @@ int tb2_plan_build(Tb2Plan &p, float *u, const float *m, const Grid &g, const Tm
     p.rows = v.rows;
     p.xchunk = xchunk;
     p.variant = vi;
+    p.lean = lean;
     p.smem_bytes = v.smem;
     p.valid = true;
     return 0;
@@ -493,7 +464,10 @@ int tb2_plan_build(Tb2Plan &p, float *u, const float *m, const Grid &g, const Tm
 int launch_stencil_tb2(const Tb2Plan &p, const Tb2Step &a, bool exact, cudaStream_t stream)
 {
     if (!p.valid) return (int)cudaErrorInvalidValue;
-    const Tb2Variant &v = g_tb2[p.variant];
+    int ntab = g_ntb2;
+    const Tb2Variant *tab = g_tb2;
+    if (p.lean) tab = tb2l_variants(&ntab);
+    const Tb2Variant &v = tab[p.variant];
     if (v.exact != exact) return (int)cudaErrorInvalidValue;
     const int ny = a.g.Y1 - a.g.Y0, nz = a.g.Z1 - a.g.Z0, nx = a.g.X1 - a.g.X0;
     if (nx <= 0) return 0;

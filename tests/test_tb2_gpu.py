@@ -68,18 +68,20 @@ def run_plan(pkg, u, m, src, crd, *, options, time_m=0, time_M=None, h=0.1, spli
     return out, t, info
 
 
-TILES = [(32, 64, 1), (28, 64, 1), (16, 128, 1), (16, 64, 1), (32, 64, 2), (16, 128, 2)]  # (TY, TZ, rows per thread)
+# (TY, TZ, rows per thread, lean): lean = 1 is stencil_tb2l.cu (the default), lean = 0 stencil_tb2.cu (the only one with two rows per thread)
+TILES = [(32, 64, 1, 1), (28, 64, 1, 1), (16, 128, 1, 1), (16, 64, 1, 1), (32, 64, 1, 0), (28, 64, 1, 0), (16, 128, 1, 0), (16, 64, 1, 0),
+         (32, 64, 2, 0), (16, 128, 2, 0)]
 
 
-@pytest.mark.parametrize("ty,tz,rows", TILES)
-def test_two_step_pass_bit_exact(pkg, oracle, ty, tz, rows):
-    """Every instantiation on a grid that is not a multiple of the tile, several x chunks, random m, sources
-    (coincident ones too) -- exact arithmetic: 0 ulp vs the oracle; contracted: 0 ulp vs the one-step kernel."""
+@pytest.mark.parametrize("ty,tz,rows,lean", TILES)
+def test_two_step_pass_bit_exact(pkg, oracle, ty, tz, rows, lean):
+    """Every instantiation of both two-step kernels on a grid that is not a multiple of the tile, several x chunks, random m,
+    sources (coincident ones too) -- exact arithmetic: 0 ulp vs the oracle; contracted: 0 ulp vs the one-step kernel."""
     shape, T, S = (23, 44, 72), 11, 6
     u, m, src, crd = fused_case(200 + ty + tz, shape, T, S)
     ref = u.copy()
     oracle.run(ref, m, src, crd, impl="port")
-    opts = {"kernel": 2, "t_fuse": 2, "tile_y": ty, "tile_z": tz, "rows": rows, "xchunk": 9}
+    opts = {"kernel": 2, "t_fuse": 2, "tile_y": ty, "tile_z": tz, "rows": rows, "xchunk": 9, "tb2_lean": lean}
     out, t, info = run_plan(pkg, u, m, src, crd, options=dict(opts, exact=1))
     assert info["t_fuse_used"] == 2 and (info["tile_y_used"], info["tile_z_used"]) == (ty, tz)
     assert info["launches"] < T + 1  # steps were actually paired (T one-step launches + the mbase gather otherwise)

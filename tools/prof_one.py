@@ -14,6 +14,7 @@ ap.add_argument("--rows", type=int, default=0)
 ap.add_argument("--xchunk", type=int, default=0)
 ap.add_argument("--steps", type=int, default=6)
 ap.add_argument("--cluster", type=int, default=0)
+ap.add_argument("--lean", type=int, default=1)
 a = ap.parse_args()
 n, T = a.n, a.steps + 5
 src, crd = pkg.fill_ricker(T, 1), pkg.fill_source_coords(1, n, n, n)
@@ -23,6 +24,7 @@ with pkg.Plan(n, n, n, deviceid=0) as p:
     p.set_option("t_fuse", a.tfuse)
     p.set_option("exact", a.exact)
     p.set_option("cluster", a.cluster)
+    p.set_option("tb2_lean", a.lean)
     if a.tile:
         ty, tz = [int(x) for x in a.tile.split("x")]
         p.set_option("tile_y", ty)

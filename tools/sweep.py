@@ -32,6 +32,7 @@ def main():
     ap.add_argument("--global-nx", type=int, default=0, help="place the source lattice as if the slab were part of this global grid")
     ap.add_argument("--dense", action="store_true", help="dense sin field instead of the zero field")
     ap.add_argument("--tfuse", type=int, default=1, help="2: two-step passes (tiles are then the output tiles TYxTZ of stencil_tb2.cu)")
+    ap.add_argument("--lean", type=int, default=1, help="two-step passes: 1 = stencil_tb2l.cu, 0 = stencil_tb2.cu")
     ap.add_argument("--cluster", type=int, default=0, help="1: two-step passes on 2-CTA clusters (stencil_tc2.cu)")
     a = ap.parse_args()
     n, T = a.n, a.steps + 5
@@ -55,7 +56,7 @@ def main():
                                                           [int(x) for x in a.exact.split(",")]):
             p.fill_dense() if a.dense else p.fill(0.0, 1.5)
             for k, v in (("kernel", 2), ("exact", exact), ("tile_y", ty), ("tile_z", tz), ("rows", st), ("stages", ns),
-                         ("xchunk", xc), ("t_fuse", a.tfuse), ("cluster", a.cluster)):
+                         ("xchunk", xc), ("t_fuse", a.tfuse), ("cluster", a.cluster), ("tb2_lean", a.lean)):
                 p.set_option(k, v)
             try:
                 t = p.run(0, T - 1)

@@ -26,13 +26,13 @@ static void shape_from_geometry(const fdtd_b200_geometry *geo, PlanShape &s, int
 static void grid_from_shape(const PlanShape &s, Grid &g);
 
 // ---------------------------------------------------------------------------- runtime config
-static int g_use_tc = 0, g_t_fuse = 1, g_nfields = 1;
+static int g_t_fuse = 1;
 
 extern "C" void FDTD_SetRuntimeConfig(int use_tc, int t_fuse, int nfields)
 {
-    g_use_tc = use_tc;                       // accepted, ignored: the stencil is not a contraction
+    (void)use_tc;                            // accepted, ignored: the stencil is not a contraction
     g_t_fuse = t_fuse < 1 ? 1 : t_fuse;      // temporal-blocking depth requested by the driver
-    g_nfields = nfields < 1 ? 1 : nfields;   // only 1 field is supported; larger values are ignored
+    (void)nfields;                           // only 1 field is supported; larger values are ignored
 }
 
 int fdtd::env_int(const char *key, int fallback)
@@ -896,10 +896,16 @@ static int plan_fuse_feasible(fdtd_b200_plan *p, int *out)
 {
     *out = 1;
     if (p->opt_t_fuse < 2 || p->opt_kernel == 1 || p->shape.space_order != 4 || !tma_supported(p->g)) return 0;
-    // In bit-exact arithmetic a two-step pass is SLOWER than two one-step launches (245 vs 393 Gpts/s at 512^3: the IEEE
-    // division and the unfused chain make the pass issue-bound).  The driver's FDTD_TFUSE (main.cpp:266-276) is a request
-    // for speed, not for a schedule: with exact arithmetic it is honoured only when set explicitly through set_option.
-    if (p->opt_exact && !p->t_fuse_explicit) return 0;
+    // In bit-exact arithmetic a two-step pass of the FIRST kernel (stencil_tb2.cu) is slower than two one-step launches (245 vs
+    // 393 Gpts/s at 512^3), the lean kernel's is faster (416).  The driver's FDTD_TFUSE (main.cpp:266-276) is a request for
+    // speed, not for a schedule: with exact arithmetic and the first kernel it is honoured only when set explicitly.
+    // Where the wavefield's fringe (tiny and denormal dividends: the division's slow paths) is a large part of the grid, the pass
+    // is slower again -- its warps advance in lock step, so one slow warp holds up the tile (256^3, T=50: 264 vs 327): below 64 M
+    // points the same rule applies to the lean kernel.
+    if (p->opt_exact && !p->t_fuse_explicit) {
+        const long long pts = (long long)(p->g.X1 - p->g.X0) * (p->g.Y1 - p->g.Y0) * (p->g.Z1 - p->g.Z0);
+        if (!(p->cfg.lean != 0 && p->cfg.rows != 2) || pts < (64LL << 20)) return 0;
+    }
     const bool linked = p->link.peer_u[0] || p->link.peer_u[1];
     // receivers on linked slabs read a ghost plane of u^{n+1} that the neighbour's SAME pass writes: one-step passes
     // (nrec_total is the same on every slab, so all slabs decide alike)

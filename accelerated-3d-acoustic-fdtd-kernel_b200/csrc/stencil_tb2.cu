@@ -27,6 +27,7 @@
 #include "stencil_tb2.cuh"
 
 #include <math.h>
+#include <stdlib.h>
 
 namespace fdtd {
 
@@ -484,6 +485,10 @@ int launch_stencil_tb2(const Tb2Plan &p, const Tb2Step &a, bool exact, cudaStrea
     args.tiles_y = (ny + p.ty - 1) / p.ty;
     args.xchunk = p.xchunk;
     args.edge = 0;
+    // L2 prefetch distance of the lean kernel's producer: 2 stages in contracted arithmetic (509 -> 547 Gpts/s at 512^3), none in
+    // exact arithmetic (issue-bound: 413 without, 395 with) -- profiles/r02_sweep512_lean_prefetch.txt
+    static const int pf = [] { const char *e = getenv("FDTD_B200_TB2_PREFETCH"); return e ? atoi(e) : -1; }();
+    args.prefetch = pf >= 0 ? pf : (exact ? 0 : 2);
     int nchunks = (nx + p.xchunk - 1) / p.xchunk;
     const bool linked = a.link.peer_u[0] != nullptr || a.link.peer_u[1] != nullptr;
     if (linked) {  // short boundary chunks hold the 4 planes a neighbour needs; the usual chunks lie in between

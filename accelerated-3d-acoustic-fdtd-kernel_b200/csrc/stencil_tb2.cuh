@@ -15,6 +15,7 @@ struct Tb2Args {
     Tb2Step s;
     int tiles_z, tiles_y, xchunk;
     int edge;  // > 0: the first and last chunk are `edge` planes long (slabs with neighbours)
+    int prefetch;  // lean kernel: stages the producer prefetches into L2 ahead of its loads (0 = none)
 };
 
 // Source cells of one plane that fall into this thread's float4: add their contributions in p_src order.

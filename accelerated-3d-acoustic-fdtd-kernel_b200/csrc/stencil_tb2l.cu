@@ -134,7 +134,7 @@ __device__ __noinline__ float4 tb2l_rare(float4 v, const Tb2Args *a, int step, i
 // MODE 0: neither source cells in the chunk nor a slab boundary; 1: a CTA on ONE boundary of a linked slab (copies its boundary
 // planes into that neighbour's ghost planes, whose address is the own one + a launch constant); 2: source cells in the chunk, or
 // both boundaries in one chunk (tb2l_rare() per step).
-template <int ER, int EC, bool EXACT, int MODE>
+template <int ER, int EC, bool EXACT, int MODE, bool HOIST>
 __device__ __forceinline__ void tb2l_consume(const Tb2Args &a, const uint32_t s0, const int Xa, const int Xb, const int Yt, const int Zt,
                                              const int XC0, const int XC1, const int xs_lo, const int xs_hi)
 {
@@ -221,6 +221,20 @@ __device__ __forceinline__ void tb2l_consume(const Tb2Args &a, const uint32_t s0
         mbar_wait_at<FULL + 8 * fsl>(s0, ((I + 4) / 5) & 1);
         if (STEP2) mbar_wait_at<DONE + 8 * bsl>(s0, ((I - 2) / 5) & 1);  // all warps have finished iteration i-2
         qU[fsl] = lds4<TB2L_U(fsl, 0, 0)>(sb);
+        // step 2's shared-memory operands (the step-1 plane of iteration i-2 and its m) do not depend on this iteration's step 1:
+        // HOIST issues their loads before step 1's arithmetic.  Not instantiated: at the 80 registers a 23-warp CTA gets, the 28
+        // extra live registers spill (3.6 KB of spill stores per thread).
+        float4 t_ym2, t_ym1, t_yp1, t_yp2, t_mv;
+        float2 t_zl, t_zr;
+        auto load2 = [&]() __attribute__((always_inline)) {
+            t_ym2 = lds4<TB2L_C(T::OFF_B, bsl, -2, 0)>(sb), t_ym1 = lds4<TB2L_C(T::OFF_B, bsl, -1, 0)>(sb);
+            t_yp1 = lds4<TB2L_C(T::OFF_B, bsl, 1, 0)>(sb), t_yp2 = lds4<TB2L_C(T::OFF_B, bsl, 2, 0)>(sb);
+            t_zl = lds2<TB2L_C(T::OFF_B, bsl, 0, -2)>(sb), t_zr = lds2<TB2L_C(T::OFF_B, bsl, 0, 4)>(sb);
+            t_mv = lds4<TB2L_C(T::OFF_M, bsl, 0, 0)>(sb);  // m of plane Xa+i-4: loaded with iteration i-2
+        };
+        if (STEP2 && HOIST) {
+            if (warp_core) load2();
+        }
         // ---------------- step 1: u^{n+1} on plane Xa-2+i, extended tile
         float4 res;
         {
@@ -249,12 +263,10 @@ __device__ __forceinline__ void tb2l_consume(const Tb2Args &a, const uint32_t s0
         // ---------------- step 2: u^{n+2} on plane Xa+i-4 (centre = step-1 plane of iteration i-2)
         if (STEP2) {
             if (warp_core) {
-                const float4 ym2 = lds4<TB2L_C(T::OFF_B, bsl, -2, 0)>(sb), ym1 = lds4<TB2L_C(T::OFF_B, bsl, -1, 0)>(sb);
-                const float4 yp1 = lds4<TB2L_C(T::OFF_B, bsl, 1, 0)>(sb), yp2 = lds4<TB2L_C(T::OFF_B, bsl, 2, 0)>(sb);
-                const float2 zl = lds2<TB2L_C(T::OFF_B, bsl, 0, -2)>(sb), zr = lds2<TB2L_C(T::OFF_B, bsl, 0, 4)>(sb);
-                const float4 mv = lds4<TB2L_C(T::OFF_M, bsl, 0, 0)>(sb);  // m of plane Xa+i-4: loaded with iteration i-2
+                if (!HOIST) load2();
                 // x neighbours and centre from the step-1 queue; "previous" level = u^n on this plane (stage i, slot k)
-                float4 o = column4<EXACT>(qR[bsl], qR[(k + 1) % 5], qR[(k + 2) % 5], qR[(k + 4) % 5], qR[k], ym2, ym1, yp1, yp2, zl, zr, qU[k], mv, a.s.k);
+                float4 o = column4<EXACT>(qR[bsl], qR[(k + 1) % 5], qR[(k + 2) % 5], qR[(k + 4) % 5], qR[k], t_ym2, t_ym1, t_yp1, t_yp2, t_zl, t_zr, qU[k],
+                                          t_mv, a.s.k);
                 if (MODE == 2) {
                     if ((X1 - 2 >= xs_lo && X1 - 2 <= xs_hi) || pushes) o = tb2l_rare(o, &a, 1, X1 - 2, Y, Z, core ? 1 : 0);
                 }
@@ -305,8 +317,8 @@ __device__ __forceinline__ void tb2l_consume(const Tb2Args &a, const uint32_t s0
 #undef TB2L_C
 }
 
-template <int ER, int EC, bool EXACT, int LB = 0>  // LB: launch bound override (experiments with the register cap)
-__global__ void __launch_bounds__(LB ? LB : Tb2LShape<ER, EC>::NT, 1) stencil_tb2l_kernel(const __grid_constant__ Tb2Args a)
+template <int ER, int EC, bool EXACT, bool HOIST = false>
+__global__ void __launch_bounds__(Tb2LShape<ER, EC>::NT, 1) stencil_tb2l_kernel(const __grid_constant__ Tb2Args a)
 {
     using T = Tb2LShape<ER, EC>;
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -378,7 +390,19 @@ __global__ void __launch_bounds__(LB ? LB : Tb2LShape<ER, EC>::NT, 1) stencil_tb
             const int nst = nit + 4;
             int us = 0, cs = 0;
             bool waited[2] = {tiled || !(lk.wait && lk.peer_u[0]), tiled || !(lk.wait && lk.peer_u[1])};
+            // L2 prefetch of stage t (own planes only: a neighbour's ghost planes may not have been written yet)
+            auto prefetch = [&](int t) {
+                const int Xt = Xa - 4 + t;
+                if (Xt >= g.X0 && Xt < g.X1) tma_prefetch_4d(&a.map_cur, Zt - 4, Yt - 4, Xt, a.s.l_cur);
+                if (Xt - 2 >= g.X0 && Xt - 2 < g.X1) {
+                    tma_prefetch_4d(&a.map_prev, Zt - 4, Yt - 2, Xt - 2, a.s.l_prev);
+                    tma_prefetch_3d(&a.map_m, Zt - 4, Yt - 2, Xt - 2);
+                }
+            };
+            const int pf = a.prefetch;
+            for (int t = 5; t < 5 + pf && t < nst; ++t) prefetch(t);
             for (int s = 0; s < nst; ++s) {
+                if (pf > 0 && s >= 5 && s + pf < nst) prefetch(s + pf);
                 const int Xp = Xa - 4 + s;  // ghost planes (outside [X0, X1)) are written by the neighbours' previous pass
                 const int side = Xp < g.X0 ? 0 : (Xp >= g.X1 ? 1 : -1);
                 if (side >= 0 && !waited[side]) {
@@ -421,11 +445,11 @@ __global__ void __launch_bounds__(LB ? LB : Tb2LShape<ER, EC>::NT, 1) stencil_tb
     const bool cta_lo = lk.peer_u[0] != nullptr && Xa < g.X0 + 4;
     const bool cta_hi = lk.peer_u[1] != nullptr && Xb > g.X1 - 4;
     if (has_src || (cta_lo && cta_hi && !lk.pull))
-        tb2l_consume<ER, EC, EXACT, 2>(a, s0, Xa, Xb, Yt, Zt, XC0, XC1, xs_lo, xs_hi);
+        tb2l_consume<ER, EC, EXACT, 2, HOIST>(a, s0, Xa, Xb, Yt, Zt, XC0, XC1, xs_lo, xs_hi);
     else if ((cta_lo || cta_hi) && !lk.pull)
-        tb2l_consume<ER, EC, EXACT, 1>(a, s0, Xa, Xb, Yt, Zt, XC0, XC1, 0, -1);
+        tb2l_consume<ER, EC, EXACT, 1, HOIST>(a, s0, Xa, Xb, Yt, Zt, XC0, XC1, 0, -1);
     else
-        tb2l_consume<ER, EC, EXACT, 0>(a, s0, Xa, Xb, Yt, Zt, XC0, XC1, 0, -1);
+        tb2l_consume<ER, EC, EXACT, 0, HOIST>(a, s0, Xa, Xb, Yt, Zt, XC0, XC1, 0, -1);
 
     if (cta_lo || cta_hi) {
         // every consumer thread of this CTA has issued its peer stores: count the CTA, and let the last CTA of
@@ -457,7 +481,6 @@ static const Tb2Variant g_tb2l[] = {
     FDTD_TB2L(32, 18),  // 28 x 64
     FDTD_TB2L(20, 34),  // 16 x 128
     FDTD_TB2L(20, 18),  // 16 x 64
-    {32, 18, 3, false, stencil_tb2l_kernel<32, 18, false, 736>, Tb2LShape<32, 18>::NT, (size_t)Tb2LShape<32, 18>::SMEM},  // experiment: 28 x 64 at 80 registers ("rows" = 3)
 };
 const Tb2Variant *tb2l_variants(int *n)
 {

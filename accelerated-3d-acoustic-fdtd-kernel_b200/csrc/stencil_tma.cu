@@ -109,14 +109,27 @@ __global__ void __launch_bounds__(TileShape<TY, TZ, RY, NS>::NT, MINB)
     const int Yt = g.Y0 + ty * TY;  // padded origin of the tile
     const int Zt = g.Z0 + tz * TZ;
 
+    // Does any source cell of this chunk lie inside this TILE?  (Asking per chunk only sent every tile of the source's chunks --
+    // a quarter of the CTAs at 512^3 -- through two dependent global loads per plane.)
+    __shared__ int s_tile_has_src;
     if (threadIdx.x == 0) {
         for (int i = 0; i < S0; ++i) {
             mbar_init(full0 + 8 * i, 1);
             mbar_init(empty0 + 8 * i, T::NCW);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        s_tile_has_src = 0;
     }
     __syncthreads();
+    if (a.s.sv.ncells > 0) {
+        const int c0 = a.s.sv.plane_off[Xa], c1 = a.s.sv.plane_off[Xb];
+        for (int q = c0 + (int)threadIdx.x; q < c1; q += T::NT) {
+            const SourceCell cell = a.s.sv.cells[q];
+            if (cell.Y >= Yt && cell.Y < Yt + TY && cell.Z >= Zt && cell.Z < Zt + TZ) s_tile_has_src = 1;
+        }
+        __syncthreads();
+    }
+    const bool chunk_has_src = s_tile_has_src != 0;
 
     if (threadIdx.x >= T::NC) {
         // ------------------------------------------------------------------ producer (one thread)
@@ -172,8 +185,6 @@ __global__ void __launch_bounds__(TileShape<TY, TZ, RY, NS>::NT, MINB)
     constexpr int HSLOT_F = T::HSLOT / 4;
 
     const SourceView &sv = a.s.sv;
-    bool chunk_has_src = false;
-    if (sv.ncells > 0) chunk_has_src = (sv.plane_off[Xb] - sv.plane_off[Xa]) > 0;
 
     // Register queue: q[s % 5][r] = this thread's float4 of u[t0] plane (stage s), row r.  All indices are
     // compile-time constants because the plane loop is unrolled by the ring period.

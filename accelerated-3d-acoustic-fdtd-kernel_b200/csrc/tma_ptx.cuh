@@ -55,6 +55,17 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map
         ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
+// The same boxes brought into L2 only (no shared-memory slot, no barrier): issued a few stages ahead of the load itself, so that
+// the load's latency is an L2 hit and the DRAM latency (and its jitter) is hidden without a deeper shared-memory ring.
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap *map, int c0, int c1, int c2, int c3)
+{
+    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"((uint64_t)map), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap *map, int c0, int c1, int c2)
+{
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"((uint64_t)map), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
 // Spin (bounded) until *flag >= want; the neighbour stores the flag with release.sys after its
 // boundary planes have landed in this GPU's memory.  On timeout mark *err and carry on.
 __device__ __forceinline__ void wait_flag(const int *flag, int want, int *err)

@@ -144,10 +144,9 @@ def test_falls_back_when_a_source_touches_a_halo(pkg, oracle):
 
 
 def test_benchmark_config_matches_golden_with_two_step_passes(pkg, oracle, golden):
-    """The driver's benchmark inputs through the reference ABI with FDTD_SetRuntimeConfig(t_fuse = 2).  With the library's
-    default bit-exact arithmetic the hook's t_fuse is advisory (an exact two-step pass is slower than two one-step launches):
-    one-step launches run and the result is still the golden one; with FDTD_B200_EXACT=0 the same call runs two-step passes
-    (tests below cover their parity)."""
+    """The driver's benchmark inputs through the reference ABI with FDTD_SetRuntimeConfig(t_fuse = 2): two-step passes of the lean
+    kernel in the library's default bit-exact arithmetic (with FDTD_B200_TB2_LEAN=0 the hook's t_fuse would be advisory: an exact
+    pass of the first two-step kernel is slower than two one-step launches); the result is the golden one either way."""
     import hashlib
 
     meta, _ = golden

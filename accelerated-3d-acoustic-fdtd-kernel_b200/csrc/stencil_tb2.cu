@@ -500,6 +500,12 @@ int launch_stencil_tb2(const Tb2Plan &p, const Tb2Step &a, bool exact, cudaStrea
                 args.xchunk = (nx + nchunks - 1) / nchunks;
             }
             nchunks = (nx + args.xchunk - 1) / args.xchunk;
+            // lean kernel: a CTA that holds BOTH boundaries runs the loop copy with calls (stencil_tb2l.cu, MODE 2); two chunks keep
+            // every CTA of a slab with two neighbours on the one-boundary copy (2048^3 on 8 GPUs: 1320 -> see profiles)
+            if (p.lean && nchunks == 1 && a.link.peer_u[0] != nullptr && a.link.peer_u[1] != nullptr && nx >= 16) {
+                nchunks = 2;
+                args.xchunk = (nx + 1) / 2;
+            }
         } else {
             args.edge = slab_edge_planes(nx, p.xchunk, args.tiles_z * args.tiles_y, 0);
             nchunks = 2 + (nx - 2 * args.edge + p.xchunk - 1) / p.xchunk;

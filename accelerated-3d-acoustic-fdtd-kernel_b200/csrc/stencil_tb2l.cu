@@ -51,6 +51,8 @@ struct Tb2LShape {
     static_assert(SMEM <= 232448, "shared memory of one CTA exceeds 227 KB");
 };
 
+constexpr int kSrcMaskWords = 64;  // planes per chunk the per-tile source-plane mask covers (32 per word)
+
 // ---- shared-memory accesses as [register + immediate]
 template <int OFF>
 __device__ __forceinline__ float4 lds4(uint32_t base)
@@ -136,7 +138,7 @@ __device__ __noinline__ float4 tb2l_rare(float4 v, const Tb2Args *a, int step, i
 // both boundaries in one chunk (tb2l_rare() per step).
 template <int ER, int EC, bool EXACT, int MODE, bool HOIST>
 __device__ __forceinline__ void tb2l_consume(const Tb2Args &a, const uint32_t s0, const int Xa, const int Xb, const int Yt, const int Zt,
-                                             const int XC0, const int XC1, const int xs_lo, const int xs_hi)
+                                             const int XC0, const int XC1, const int xs_lo, const int xs_hi, const unsigned *srcmask)
 {
     using T = Tb2LShape<ER, EC>;
     constexpr int HP = T::HP;
@@ -179,6 +181,13 @@ __device__ __forceinline__ void tb2l_consume(const Tb2Args &a, const uint32_t s0
     const SlabLink &lk = a.s.link;
     // MODE 2: a boundary CTA (one side with source cells, or both sides in one chunk) copies its boundary planes inside tb2l_rare()
     const bool pushes = MODE == 2 && !lk.pull && ((lk.peer_u[0] != nullptr && Xa < g.X0 + 4) || (lk.peer_u[1] != nullptr && Xb > g.X1 - 4));
+    // MODE 2: does plane X hold a source cell inside this tile?  (a 64-source lattice puts cells into many tiles, but into few
+    // planes of each: asking per plane keeps the call out of almost every iteration)
+    auto plane_has_src = [&](int X) -> bool {
+        if (X < xs_lo || X > xs_hi) return false;
+        const int j = X - (Xa - 2);
+        return j >= 32 * kSrcMaskWords || ((srcmask[j >> 5] >> (j & 31)) & 1u);
+    };
     unsigned long long dq1 = 0, dq2 = 0;
     int W = 0, wstep = 0, thr1 = 0, thr2 = 0;
     if (MODE == 1) {
@@ -245,7 +254,7 @@ __device__ __forceinline__ void tb2l_consume(const Tb2Args &a, const uint32_t s0
             float4 v = column4<EXACT>(qU[csl], qU[k], qU[(k + 1) % 5], qU[(k + 3) % 5], qU[fsl], ym2, ym1, yp1, yp2, zl, zr, pv, mv, a.s.k);
             const bool st = core && (FIRST ? J >= 2 : true) && rem > 2;
             if (MODE == 2) {
-                if ((X1 >= xs_lo && X1 <= xs_hi) || pushes) v = tb2l_rare(v, &a, 0, X1, Y, Z, st ? 1 : 0);
+                if (plane_has_src(X1) || (pushes && (X1 < g.X0 + 2 || X1 >= g.X1 - 2))) v = tb2l_rare(v, &a, 0, X1, Y, Z, st ? 1 : 0);
             }
             if (st) stg4(p1, v);
             if (MODE == 1) {
@@ -268,7 +277,7 @@ __device__ __forceinline__ void tb2l_consume(const Tb2Args &a, const uint32_t s0
                 float4 o = column4<EXACT>(qR[bsl], qR[(k + 1) % 5], qR[(k + 2) % 5], qR[(k + 4) % 5], qR[k], t_ym2, t_ym1, t_yp1, t_yp2, t_zl, t_zr, qU[k],
                                           t_mv, a.s.k);
                 if (MODE == 2) {
-                    if ((X1 - 2 >= xs_lo && X1 - 2 <= xs_hi) || pushes) o = tb2l_rare(o, &a, 1, X1 - 2, Y, Z, core ? 1 : 0);
+                    if (plane_has_src(X1 - 2) || (pushes && (X1 < g.X0 + 6 || X1 >= g.X1 - 2))) o = tb2l_rare(o, &a, 1, X1 - 2, Y, Z, core ? 1 : 0);
                 }
                 if (core) stg4(p1 + d2, o);
                 if (MODE == 1) {
@@ -354,6 +363,8 @@ __global__ void __launch_bounds__(Tb2LShape<ER, EC>::NT, 1) stencil_tb2l_kernel(
     // Which planes of this chunk (incl. its ghost-zone planes) hold source cells inside this tile's extended (y,z) range?  Almost
     // always none: then the CTA runs the copy of the loop without injection.
     __shared__ int s_xsrc[2];
+    __shared__ unsigned s_srcmask[kSrcMaskWords];  // bit j: plane Xa-2+j holds such a cell (chunks longer than the mask: every plane is asked)
+    if (threadIdx.x < kSrcMaskWords) s_srcmask[threadIdx.x] = 0u;
     if (threadIdx.x == 0) {
         for (int i = 0; i < T::D; ++i) mbar_init(s0 + FULL + 8 * i, 1);
         for (int i = 0; i < T::D; ++i) mbar_init(s0 + DONE + 8 * i, T::NCW);
@@ -370,6 +381,8 @@ __global__ void __launch_bounds__(Tb2LShape<ER, EC>::NT, 1) stencil_tb2l_kernel(
             if (cell.Y >= Yt - 2 && cell.Y < Yt + T::TY + 2 && cell.Z >= Zt - 4 && cell.Z < Zt + T::TZ + 4) {
                 atomicMin(&s_xsrc[0], cell.X);
                 atomicMax(&s_xsrc[1], cell.X);
+                const int j = cell.X - (Xa - 2);
+                if (j < 32 * kSrcMaskWords) atomicOr(&s_srcmask[j >> 5], 1u << (j & 31));
             }
         }
         __syncthreads();
@@ -445,11 +458,11 @@ __global__ void __launch_bounds__(Tb2LShape<ER, EC>::NT, 1) stencil_tb2l_kernel(
     const bool cta_lo = lk.peer_u[0] != nullptr && Xa < g.X0 + 4;
     const bool cta_hi = lk.peer_u[1] != nullptr && Xb > g.X1 - 4;
     if (has_src || (cta_lo && cta_hi && !lk.pull))
-        tb2l_consume<ER, EC, EXACT, 2, HOIST>(a, s0, Xa, Xb, Yt, Zt, XC0, XC1, xs_lo, xs_hi);
+        tb2l_consume<ER, EC, EXACT, 2, HOIST>(a, s0, Xa, Xb, Yt, Zt, XC0, XC1, xs_lo, xs_hi, s_srcmask);
     else if ((cta_lo || cta_hi) && !lk.pull)
-        tb2l_consume<ER, EC, EXACT, 1, HOIST>(a, s0, Xa, Xb, Yt, Zt, XC0, XC1, 0, -1);
+        tb2l_consume<ER, EC, EXACT, 1, HOIST>(a, s0, Xa, Xb, Yt, Zt, XC0, XC1, 0, -1, s_srcmask);
     else
-        tb2l_consume<ER, EC, EXACT, 0, HOIST>(a, s0, Xa, Xb, Yt, Zt, XC0, XC1, 0, -1);
+        tb2l_consume<ER, EC, EXACT, 0, HOIST>(a, s0, Xa, Xb, Yt, Zt, XC0, XC1, 0, -1, s_srcmask);
 
     if (cta_lo || cta_hi) {
         // every consumer thread of this CTA has issued its peer stores: count the CTA, and let the last CTA of

@@ -439,7 +439,9 @@ int tb2_plan_build(Tb2Plan &p, float *u, const float *m, const Grid &g, const Tm
     int xchunk = cfg.xchunk;
     if (xchunk <= 0) {
         double best = -1.0;
-        for (int nch = 1; nch <= nx; ++nch) {
+        // chunks longer than 128 planes run slower (1024^3, lean kernel: 549 Gpts/s at 64 and 128 planes, 481 at 256, 440 at 512 --
+        // profiles/r02_sweep1024_lean.txt: neighbouring tiles drift apart along x and stop sharing their halo rows in L2)
+        for (int nch = (nx + 127) / 128; nch <= nx; ++nch) {
             const int xc = (nx + nch - 1) / nch;
             if (xc < 16 && nch > 1) break;
             if ((nx + xc - 1) / xc != nch) continue;

@@ -136,7 +136,7 @@ __device__ __noinline__ float4 tb2l_rare(float4 v, const Tb2Args *a, int step, i
 // MODE 0: neither source cells in the chunk nor a slab boundary; 1: a CTA on ONE boundary of a linked slab (copies its boundary
 // planes into that neighbour's ghost planes, whose address is the own one + a launch constant); 2: source cells in the chunk, or
 // both boundaries in one chunk (tb2l_rare() per step).
-template <int ER, int EC, bool EXACT, int MODE, bool HOIST>
+template <int ER, int EC, bool EXACT, int MODE>
 __device__ __forceinline__ void tb2l_consume(const Tb2Args &a, const uint32_t s0, const int Xa, const int Xb, const int Yt, const int Zt,
                                              const int XC0, const int XC1, const int xs_lo, const int xs_hi, const unsigned *srcmask)
 {
@@ -217,6 +217,17 @@ __device__ __forceinline__ void tb2l_consume(const Tb2Args &a, const uint32_t s0
     mbar_wait_at<FULL + 24>(s0, 0);
     qU[3] = lds4<TB2L_U(3, 0, 0)>(sb);
 
+    // The two floats left (zl) and right (zr) of the own float4: 8-byte loads at a 16-byte lane stride touch half of the banks and
+    // take 4 wavefronts instead of 2 -- all of the kernel's bank conflicts (10.7 M of 94 M wavefronts per pass,
+    // profiles/r02_ncu_tb2l_16x128_exact0.txt).  Letting odd groups of 8 lanes read zr first and zl second makes both loads
+    // conflict-free, but the selects and the two extra base registers cost what the wavefronts gain (539 vs 542 Gpts/s,
+    // profiles/r02_sweep512_zswap.txt): not kept.
+    auto load_z = [&](float2 &zl, float2 &zr, auto offc) __attribute__((always_inline)) {
+        constexpr int OFF = decltype(offc)::value;
+        zl = lds2<OFF - 8>(sb);
+        zr = lds2<OFF + 16>(sb);
+    };
+
     // Iteration i (k = i % 5): new u^n stage i+4 -> slot (k+4)%5; centre plane of step 1 = stage i+2 -> slot (k+2)%5; u^{n-1}, m and
     // the step-1 result of iteration i -> slot k; step 2 works on the step-1 plane of iteration i-2 -> slot (k+3)%5.  The first
     // five iterations are peeled (I0 = 0), then the loop is unrolled by ten (i = 5 + 10*G + J) so that the barrier parities
@@ -230,26 +241,13 @@ __device__ __forceinline__ void tb2l_consume(const Tb2Args &a, const uint32_t s0
         mbar_wait_at<FULL + 8 * fsl>(s0, ((I + 4) / 5) & 1);
         if (STEP2) mbar_wait_at<DONE + 8 * bsl>(s0, ((I - 2) / 5) & 1);  // all warps have finished iteration i-2
         qU[fsl] = lds4<TB2L_U(fsl, 0, 0)>(sb);
-        // step 2's shared-memory operands (the step-1 plane of iteration i-2 and its m) do not depend on this iteration's step 1:
-        // HOIST issues their loads before step 1's arithmetic.  Not instantiated: at the 80 registers a 23-warp CTA gets, the 28
-        // extra live registers spill (3.6 KB of spill stores per thread).
-        float4 t_ym2, t_ym1, t_yp1, t_yp2, t_mv;
-        float2 t_zl, t_zr;
-        auto load2 = [&]() __attribute__((always_inline)) {
-            t_ym2 = lds4<TB2L_C(T::OFF_B, bsl, -2, 0)>(sb), t_ym1 = lds4<TB2L_C(T::OFF_B, bsl, -1, 0)>(sb);
-            t_yp1 = lds4<TB2L_C(T::OFF_B, bsl, 1, 0)>(sb), t_yp2 = lds4<TB2L_C(T::OFF_B, bsl, 2, 0)>(sb);
-            t_zl = lds2<TB2L_C(T::OFF_B, bsl, 0, -2)>(sb), t_zr = lds2<TB2L_C(T::OFF_B, bsl, 0, 4)>(sb);
-            t_mv = lds4<TB2L_C(T::OFF_M, bsl, 0, 0)>(sb);  // m of plane Xa+i-4: loaded with iteration i-2
-        };
-        if (STEP2 && HOIST) {
-            if (warp_core) load2();
-        }
         // ---------------- step 1: u^{n+1} on plane Xa-2+i, extended tile
         float4 res;
         {
             const float4 ym2 = lds4<TB2L_U(csl, -2, 0)>(sb), ym1 = lds4<TB2L_U(csl, -1, 0)>(sb);
             const float4 yp1 = lds4<TB2L_U(csl, 1, 0)>(sb), yp2 = lds4<TB2L_U(csl, 2, 0)>(sb);
-            const float2 zl = lds2<TB2L_U(csl, 0, -2)>(sb), zr = lds2<TB2L_U(csl, 0, 4)>(sb);
+            float2 zl, zr;
+            load_z(zl, zr, std::integral_constant<int, TB2L_U(csl, 0, 0)>{});
             const float4 pv = lds4<TB2L_C(T::OFF_P, k, 0, 0)>(sb), mv = lds4<TB2L_C(T::OFF_M, k, 0, 0)>(sb);
             float4 v = column4<EXACT>(qU[csl], qU[k], qU[(k + 1) % 5], qU[(k + 3) % 5], qU[fsl], ym2, ym1, yp1, yp2, zl, zr, pv, mv, a.s.k);
             const bool st = core && (FIRST ? J >= 2 : true) && rem > 2;
@@ -272,10 +270,13 @@ __device__ __forceinline__ void tb2l_consume(const Tb2Args &a, const uint32_t s0
         // ---------------- step 2: u^{n+2} on plane Xa+i-4 (centre = step-1 plane of iteration i-2)
         if (STEP2) {
             if (warp_core) {
-                if (!HOIST) load2();
+                const float4 ym2 = lds4<TB2L_C(T::OFF_B, bsl, -2, 0)>(sb), ym1 = lds4<TB2L_C(T::OFF_B, bsl, -1, 0)>(sb);
+                const float4 yp1 = lds4<TB2L_C(T::OFF_B, bsl, 1, 0)>(sb), yp2 = lds4<TB2L_C(T::OFF_B, bsl, 2, 0)>(sb);
+                float2 zl, zr;
+                load_z(zl, zr, std::integral_constant<int, TB2L_C(T::OFF_B, bsl, 0, 0)>{});
+                const float4 mv = lds4<TB2L_C(T::OFF_M, bsl, 0, 0)>(sb);  // m of plane Xa+i-4: loaded with iteration i-2
                 // x neighbours and centre from the step-1 queue; "previous" level = u^n on this plane (stage i, slot k)
-                float4 o = column4<EXACT>(qR[bsl], qR[(k + 1) % 5], qR[(k + 2) % 5], qR[(k + 4) % 5], qR[k], t_ym2, t_ym1, t_yp1, t_yp2, t_zl, t_zr, qU[k],
-                                          t_mv, a.s.k);
+                float4 o = column4<EXACT>(qR[bsl], qR[(k + 1) % 5], qR[(k + 2) % 5], qR[(k + 4) % 5], qR[k], ym2, ym1, yp1, yp2, zl, zr, qU[k], mv, a.s.k);
                 if (MODE == 2) {
                     if (plane_has_src(X1 - 2) || (pushes && (X1 < g.X0 + 6 || X1 >= g.X1 - 2))) o = tb2l_rare(o, &a, 1, X1 - 2, Y, Z, core ? 1 : 0);
                 }
@@ -326,7 +327,7 @@ __device__ __forceinline__ void tb2l_consume(const Tb2Args &a, const uint32_t s0
 #undef TB2L_C
 }
 
-template <int ER, int EC, bool EXACT, bool HOIST = false>
+template <int ER, int EC, bool EXACT>
 __global__ void __launch_bounds__(Tb2LShape<ER, EC>::NT, 1) stencil_tb2l_kernel(const __grid_constant__ Tb2Args a)
 {
     using T = Tb2LShape<ER, EC>;
@@ -458,11 +459,11 @@ __global__ void __launch_bounds__(Tb2LShape<ER, EC>::NT, 1) stencil_tb2l_kernel(
     const bool cta_lo = lk.peer_u[0] != nullptr && Xa < g.X0 + 4;
     const bool cta_hi = lk.peer_u[1] != nullptr && Xb > g.X1 - 4;
     if (has_src || (cta_lo && cta_hi && !lk.pull))
-        tb2l_consume<ER, EC, EXACT, 2, HOIST>(a, s0, Xa, Xb, Yt, Zt, XC0, XC1, xs_lo, xs_hi, s_srcmask);
+        tb2l_consume<ER, EC, EXACT, 2>(a, s0, Xa, Xb, Yt, Zt, XC0, XC1, xs_lo, xs_hi, s_srcmask);
     else if ((cta_lo || cta_hi) && !lk.pull)
-        tb2l_consume<ER, EC, EXACT, 1, HOIST>(a, s0, Xa, Xb, Yt, Zt, XC0, XC1, 0, -1, s_srcmask);
+        tb2l_consume<ER, EC, EXACT, 1>(a, s0, Xa, Xb, Yt, Zt, XC0, XC1, 0, -1, s_srcmask);
     else
-        tb2l_consume<ER, EC, EXACT, 0, HOIST>(a, s0, Xa, Xb, Yt, Zt, XC0, XC1, 0, -1, s_srcmask);
+        tb2l_consume<ER, EC, EXACT, 0>(a, s0, Xa, Xb, Yt, Zt, XC0, XC1, 0, -1, s_srcmask);
 
     if (cta_lo || cta_hi) {
         // every consumer thread of this CTA has issued its peer stores: count the CTA, and let the last CTA of

@@ -105,6 +105,10 @@ int launch_shell_check(float *u, const Grid &g, int *flag, cudaStream_t stream);
 // shell of level `from` -> level `to`
 int launch_shell_copy(float *u, const Grid &g, int from, int to, cudaStream_t stream);
 
+// Pull protocol: at the end of a run, copy the neighbours' four boundary planes of every device level into this slab's ghost planes
+// (waits in-kernel for the neighbours' last launch, `epoch`, to have raised this slab's whole-boundary flags).
+int launch_ghost_refresh(float *u, const Grid &g, const SlabLink &lk, int epoch, cudaStream_t stream);
+
 // --- Section1 stand-alone scatter: one thread per cell, contributions added in p_src order.
 int launch_scatter(float *u_level, const Grid &g, const SourceCell *cells, int ncells,
                    const SourceContrib *contribs, const float *src_row, const float *mbase,

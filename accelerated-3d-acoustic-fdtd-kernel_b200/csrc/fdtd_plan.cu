@@ -227,7 +227,7 @@ int fdtd::plan_create_internal(const PlanShape &s, fdtd_b200_plan **out, bool ca
     p->tile_flags_offset = p->arena_offset + kArenaBytes;
     p->u_bytes = p->tile_flags_offset + 2 * (size_t)kMaxFlagTiles * sizeof(int);
     p->opt_tile_flags = env_int("FDTD_B200_TILE_FLAGS", 1);
-    p->opt_halo_pull = env_int("FDTD_B200_HALO_PULL", 0);
+    p->opt_halo_pull = env_int("FDTD_B200_HALO_PULL", -1);
     p->m_bytes = (size_t)p->g.lvl * sizeof(float);
     const char *nc = getenv("FDTD_B200_NO_CACHE");
     p->cache_buffers = cache_buffers && !(nc && *nc == '1');
@@ -987,9 +987,6 @@ int fdtd::plan_prepare(fdtd_b200_plan *p)
     if (want == 2 && !can_tma) return (int)cudaErrorInvalidValue;
     if ((p->link.peer_u[0] || p->link.peer_u[1]) && want != 2) return (int)cudaErrorNotSupported;  // slabs need the streaming kernel
     p->kernel_used = want;
-    // receivers sample the slab's own ghost planes, which only the push protocol keeps current (nrec_total is the same on
-    // every slab, so all slabs decide alike)
-    p->link.pull = (linked && p->opt_halo_pull && p->nrec_total == 0) ? 1 : 0;
     // two time steps per pass: a lone slab decides for itself, linked slabs use the depth they agreed on
     p->t_fuse_used = 1;
     if (want == 2 && p->opt_t_fuse >= 2) {
@@ -1010,6 +1007,17 @@ int fdtd::plan_prepare(fdtd_b200_plan *p)
             if (rc) return rc;
         }
         p->t_fuse_used = depth;
+    }
+    // Halo protocol of this run.  Push: boundary planes are stored into the neighbours' ghost planes; pull: they stay where they
+    // are and the neighbours' TMA producers read them in place.  The lean two-step kernel runs its warps in lock step, so peer
+    // stores that stall hold up the whole tile: pulling is faster there (8 x 512^3: 4124 vs 3935 Gpts/s, 1024^3 on 8 GPUs: 3555 vs
+    // 3509 -- profiles/r02_slab_probe_lean.txt) and is the default for such runs; one-step runs push (measured faster in round 2).
+    // A pull run refreshes the slab's own ghost planes from the neighbours once, at its end (launch_ghost_refresh), so downloads and
+    // later runs see what a push run would have left.  Receivers sample the ghost planes during the run and need the push
+    // protocol.  Every slab sees the same options, so all slabs decide alike.
+    {
+        const bool lean2 = p->t_fuse_used == 2 && !p->use_tc2 && p->tb2.valid && p->tb2.lean;
+        p->link.pull = (linked && p->nrec_total == 0 && (p->opt_halo_pull == 1 || (p->opt_halo_pull < 0 && lean2))) ? 1 : 0;
     }
     if (want == 2 && !p->tma.valid) {
         int rc = tma_plan_build(p->tma, p->d_u, p->d_m, p->g, p->cfg, p->opt_exact != 0, p->sm_count, &p->link);
@@ -1095,6 +1103,13 @@ static int run_many(fdtd_b200_plan **ps, int n, int time_m, int time_M, struct p
     for (int i = 0; i < n; ++i) {
         if (n > 1) cudaSetDevice(ps[i]->dev);
         if (!rc && st[i].e_begin) st[i].e_end = st[i].stamp(ps[i]->stream);
+    }
+    // pull protocol: bring the slabs' own ghost planes up to date (outside the timers: once per run, 4 planes per side and level)
+    for (int i = 0; i < n && !rc; ++i) {
+        fdtd_b200_plan *p = ps[i];
+        if (!p->link.pull || p->last_kind == 0) continue;
+        if (n > 1) cudaSetDevice(p->dev);
+        rc = launch_ghost_refresh(p->d_u, p->g, p->link, p->epoch, p->stream);
     }
     double worst_total = 0.0, worst_s1 = 0.0;
     for (int i = 0; i < n; ++i) {

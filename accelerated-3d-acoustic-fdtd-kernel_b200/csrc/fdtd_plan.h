@@ -99,8 +99,8 @@ struct fdtd_b200_plan {
     int epoch = 0;                   // step sequence number, identical on every slab
     size_t tile_flags_offset = 0;    // byte offset of the per-tile flag arrays [2][kMaxFlagTiles] inside the u allocation
     int last_kind = 0;               // kernel of the previous launch of this run: 0 none, 1 one-step streaming, 2 two-step
-    int opt_halo_pull = 0;           // 1: linked slabs read the neighbours' boundary planes in place instead of receiving them
-                                     // (FDTD_B200_HALO_PULL; measured 2-5 % slower than pushing on 8 GPUs, profiles/r02_slab_protocol_ab_8gpu.txt)
+    int opt_halo_pull = -1;          // 1: linked slabs read the neighbours' boundary planes in place instead of receiving them; 0: never;
+                                     // -1 (default): for runs of the lean two-step kernel (FDTD_B200_HALO_PULL; plan_prepare)
     int opt_tile_flags = 1;          // 0: always the whole-boundary flags (FDTD_B200_TILE_FLAGS)
 
     // statistics of the last run

@@ -7,6 +7,7 @@
 // one cell and adds its contributions in p_src order (the serial order of openacc.cpp:116-136).
 #include "fdtd_arith.cuh"
 #include "fdtd_kernels.cuh"
+#include "tma_ptx.cuh"
 
 namespace fdtd {
 
@@ -242,6 +243,31 @@ int launch_fill_dense(float *u, float *m, int nxp, int nyp, int nzp, long long x
 {
     const size_t volp = (size_t)nxp * nyp * nzp;
     fill_dense_kernel<<<148 * 8, 256, 0, stream>>>(u, m, volp, (size_t)x_plane_offset * nyp * nzp);
+    return (int)cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------- ghost refresh (pull protocol)
+__global__ void ghost_refresh_kernel(float *u, Grid g, SlabLink lk, int epoch)
+{
+    const int side = blockIdx.y;
+    if (!lk.peer_u[side]) return;
+    if (threadIdx.x == 0) wait_flag(lk.my_flag[side], epoch, lk.err);  // the neighbour's last launch has written its boundary planes
+    __syncthreads();
+    const long long plane = (long long)g.nyp * g.nzp;
+    const int my_x = side == 0 ? g.X0 - FDTD_HALO : g.X1;                      // first of this slab's ghost planes on that side
+    const int peer_x = side == 0 ? lk.peer_edge[0] - FDTD_HALO : lk.peer_edge[1];  // the same planes where the neighbour computes them
+    const long long n4 = FDTD_HALO * plane / 4;
+    for (int l = 0; l < FDTD_LEVELS; ++l) {
+        const float4 *src = reinterpret_cast<const float4 *>(lk.peer_u[side] + l * lk.peer_lvl[side] + peer_x * plane);
+        float4 *dst = reinterpret_cast<float4 *>(u + l * g.lvl + my_x * plane);
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) dst[i] = src[i];
+    }
+}
+
+int launch_ghost_refresh(float *u, const Grid &g, const SlabLink &lk, int epoch, cudaStream_t stream)
+{
+    if (!lk.peer_u[0] && !lk.peer_u[1]) return 0;
+    ghost_refresh_kernel<<<dim3(128, 2), 256, 0, stream>>>(u, g, lk, epoch);
     return (int)cudaGetLastError();
 }
 

@@ -232,8 +232,9 @@ __device__ __forceinline__ void tb2l_consume(const Tb2Args &a, const uint32_t s0
     // the step-1 result of iteration i -> slot k; step 2 works on the step-1 plane of iteration i-2 -> slot (k+3)%5.  The first
     // five iterations are peeled (I0 = 0), then the loop is unrolled by ten (i = 5 + 10*G + J) so that the barrier parities
     // are compile-time constants too.
-    auto body = [&](auto jc, auto firstc) __attribute__((always_inline)) {
+    auto body = [&](auto jc, auto firstc, auto pushc) __attribute__((always_inline)) {
         constexpr bool FIRST = decltype(firstc)::value;
+        constexpr bool PUSH = MODE == 1 && decltype(pushc)::value;  // this group of iterations may hold planes the neighbour needs
         constexpr int J = decltype(jc)::value, I = (FIRST ? 0 : 5) + J, k = I % 5;  // I = i modulo 10
         constexpr bool STEP2 = !FIRST || J == 4;
         constexpr int fsl = (k + 4) % 5, csl = (k + 2) % 5, bsl = (k + 3) % 5;
@@ -255,7 +256,7 @@ __device__ __forceinline__ void tb2l_consume(const Tb2Args &a, const uint32_t s0
                 if (plane_has_src(X1) || (pushes && (X1 < g.X0 + 2 || X1 >= g.X1 - 2))) v = tb2l_rare(v, &a, 0, X1, Y, Z, st ? 1 : 0);
             }
             if (st) stg4(p1, v);
-            if (MODE == 1) {
+            if (PUSH) {
                 if (W < thr1 && st) stg4(p1 + dq1, v);
             }
             // halo cells and planes beyond a physical boundary keep their value (identical in every level by construction)
@@ -281,7 +282,7 @@ __device__ __forceinline__ void tb2l_consume(const Tb2Args &a, const uint32_t s0
                     if (plane_has_src(X1 - 2) || (pushes && (X1 < g.X0 + 6 || X1 >= g.X1 - 2))) o = tb2l_rare(o, &a, 1, X1 - 2, Y, Z, core ? 1 : 0);
                 }
                 if (core) stg4(p1 + d2, o);
-                if (MODE == 1) {
+                if (PUSH) {
                     if (W < thr2 && core) stg4(p1 + dq2, o);
                 }
             }
@@ -294,34 +295,45 @@ __device__ __forceinline__ void tb2l_consume(const Tb2Args &a, const uint32_t s0
         W += wstep;
     };
     using std::integral_constant;
-    typedef integral_constant<bool, true> First;
-    typedef integral_constant<bool, false> Steady;
-    body(integral_constant<int, 0>{}, First{});  // rem = np + 4 >= 5
-    body(integral_constant<int, 1>{}, First{});
-    body(integral_constant<int, 2>{}, First{});
-    body(integral_constant<int, 3>{}, First{});
-    body(integral_constant<int, 4>{}, First{});
+    typedef integral_constant<bool, true> Yes;
+    typedef integral_constant<bool, false> No;
+    body(integral_constant<int, 0>{}, Yes{}, Yes{});  // rem = np + 4 >= 5
+    body(integral_constant<int, 1>{}, Yes{}, Yes{});
+    body(integral_constant<int, 2>{}, Yes{}, Yes{});
+    body(integral_constant<int, 3>{}, Yes{}, Yes{});
+    body(integral_constant<int, 4>{}, Yes{}, Yes{});
+    // ten iterations; true when the chunk is finished
+    auto group = [&](auto pushc) __attribute__((always_inline)) -> bool {
+        if (rem <= 0) return true;
+        body(integral_constant<int, 0>{}, No{}, pushc);
+        if (rem <= 0) return true;
+        body(integral_constant<int, 1>{}, No{}, pushc);
+        if (rem <= 0) return true;
+        body(integral_constant<int, 2>{}, No{}, pushc);
+        if (rem <= 0) return true;
+        body(integral_constant<int, 3>{}, No{}, pushc);
+        if (rem <= 0) return true;
+        body(integral_constant<int, 4>{}, No{}, pushc);
+        if (rem <= 0) return true;
+        body(integral_constant<int, 5>{}, No{}, pushc);
+        if (rem <= 0) return true;
+        body(integral_constant<int, 6>{}, No{}, pushc);
+        if (rem <= 0) return true;
+        body(integral_constant<int, 7>{}, No{}, pushc);
+        if (rem <= 0) return true;
+        body(integral_constant<int, 8>{}, No{}, pushc);
+        if (rem <= 0) return true;
+        body(integral_constant<int, 9>{}, No{}, pushc);
+        return false;
+    };
     for (;;) {
-        if (rem <= 0) break;
-        body(integral_constant<int, 0>{}, Steady{});
-        if (rem <= 0) break;
-        body(integral_constant<int, 1>{}, Steady{});
-        if (rem <= 0) break;
-        body(integral_constant<int, 2>{}, Steady{});
-        if (rem <= 0) break;
-        body(integral_constant<int, 3>{}, Steady{});
-        if (rem <= 0) break;
-        body(integral_constant<int, 4>{}, Steady{});
-        if (rem <= 0) break;
-        body(integral_constant<int, 5>{}, Steady{});
-        if (rem <= 0) break;
-        body(integral_constant<int, 6>{}, Steady{});
-        if (rem <= 0) break;
-        body(integral_constant<int, 7>{}, Steady{});
-        if (rem <= 0) break;
-        body(integral_constant<int, 8>{}, Steady{});
-        if (rem <= 0) break;
-        body(integral_constant<int, 9>{}, Steady{});
+        // MODE 1: only the groups at the slab boundary (the first after the peeled one towards the lower neighbour, the last one or
+        // two towards the upper one) carry the peer stores; the others are the common loop
+        if (MODE == 1 && min(W, W + 9 * wstep) < thr2) {
+            if (group(Yes{})) break;
+        } else {
+            if (group(No{})) break;
+        }
     }
 #undef TB2L_U
 #undef TB2L_C

@@ -186,6 +186,10 @@ def test_many_sources_64(pkg, oracle):
     (3, (96, 36, 72), {"exact": 0}),
     (2, (80, 24, 128), {"tile_y": 16, "tile_z": 128, "xchunk": 12}),
     (4, (131, 16, 64), {"xchunk": 20}),
+    # the halo protocol is pull by default for lean two-step runs; the push protocol (peer stores from inside the kernel) and the first kernel
+    (3, (96, 36, 72), {"halo_pull": 0}),
+    (4, (131, 16, 64), {"xchunk": 20, "halo_pull": 0, "exact": 0}),
+    (3, (96, 36, 72), {"tb2_lean": 0}),
 ])
 def test_slabs_with_two_step_passes(pkg, oracle, nparts, shape, opts):
     """Several slabs on ONE device (peer pointer = local pointer): the two outermost planes of u^{n+1} and the
@@ -215,16 +219,24 @@ def test_slabs_with_two_step_passes(pkg, oracle, nparts, shape, opts):
     assert t.section0 > 0
 
 
-def test_slabs_two_step_restart(pkg, oracle):
+@pytest.mark.parametrize("pull", [-1, 0])
+def test_slabs_two_step_restart(pkg, oracle, pull):
+    """A run split in two calls; the second call runs ONE-step launches in the push protocol, which reads the slabs' own ghost
+    planes: a pull run must have refreshed them at its end."""
     shape, T, S = (64, 16, 64), 15, 4
     u, m, src, crd = fused_case(9, shape, T, S, seam_parts=2)
     ref = u.copy()
     oracle.run(ref, m, src, crd, impl="port")
-    ls = pkg.LocalSlabs(*shape, [0, 0], options={"t_fuse": 2})
+    ls = pkg.LocalSlabs(*shape, [0, 0], options={"t_fuse": 2, "halo_pull": pull})
     ls.upload(u, m)
     ls.set_sources(src, crd)
     ls.run(0, 6)
-    ls.run(7, T - 1)
+    for p in ls.plans:
+        p.set_option("t_fuse", 1)
+    ls.run(7, 10)
+    for p in ls.plans:
+        p.set_option("t_fuse", 2)
+    ls.run(11, T - 1)
     out = np.zeros_like(u)
     ls.download(out)
     ls.close()

@@ -1104,10 +1104,12 @@ static int run_many(fdtd_b200_plan **ps, int n, int time_m, int time_M, struct p
         if (n > 1) cudaSetDevice(ps[i]->dev);
         if (!rc && st[i].e_begin) st[i].e_end = st[i].stamp(ps[i]->stream);
     }
-    // pull protocol: bring the slabs' own ghost planes up to date (outside the timers: once per run, 4 planes per side and level)
+    // Bring the slabs' own ghost planes up to date, four planes deep (outside the timers: once per run).  Needed after a pull run
+    // (nothing was stored into them) and after a one-step push run (its launches store two planes per side, a two-step pass of a
+    // later run reads four).
     for (int i = 0; i < n && !rc; ++i) {
         fdtd_b200_plan *p = ps[i];
-        if (!p->link.pull || p->last_kind == 0) continue;
+        if (!(p->link.pull || p->t_fuse_used == 1) || p->last_kind == 0) continue;
         if (n > 1) cudaSetDevice(p->dev);
         rc = launch_ghost_refresh(p->d_u, p->g, p->link, p->epoch, p->stream);
     }

@@ -980,7 +980,7 @@ int fdtd::plan_prepare(fdtd_b200_plan *p)
         return 0;
     }
     // auto: the streaming kernel needs enough planes x tiles to hide its per-plane latency chain; below ~110^3
-    // points a step is a few microseconds and the one-point-per-thread kernel wins (profiles/r02_small_grids.txt)
+    // points a step is a few microseconds and the one-point-per-thread kernel wins (64^3: 4.2-5.4 us per step, `other_workloads` of profiles/r02_bench_1gpu_final.json)
     const long long npts = (long long)(p->g.X1 - p->g.X0) * (p->g.Y1 - p->g.Y0) * (p->g.Z1 - p->g.Z0);
     const bool linked = p->link.peer_u[0] || p->link.peer_u[1];
     if (want == 0) want = (can_tma && (npts >= 1400000 || linked)) ? 2 : 1;

@@ -15,11 +15,17 @@
 //   * the first group of 5 iterations (no step 2 before i = 4, no stores before i = 2) is peeled, so the steady-state body has
 //     two integer compares; step 1 is computed unconditionally and de-selected per thread where it must not apply (halo
 //     cells, planes beyond a physical boundary) instead of being branched around;
-//   * the rare work is compiled into separate copies of the loop, chosen per CTA: source cells in the chunk (a non-inlined call
-//     per step), peer stores of a boundary CTA (the neighbour's address is the own one + a launch constant); the common copy
-//     has neither, so they cost no registers and no instruction-cache footprint in the steady state.
+//   * the rare work is compiled into separate copies of the loop, chosen per CTA: source cells inside the TILE (found by a
+//     pre-pass over the chunk's cells; a non-inlined call per step, on exactly the planes that hold such a cell), peer stores of
+//     a boundary CTA in the push protocol (the neighbour's address is the own one + a launch constant); the common copy has
+//     neither, so they cost no registers and no instruction-cache footprint in the steady state;
+//   * the TMA producer prefetches a few stages ahead into L2 (cp.async.bulk.prefetch.tensor): DRAM latency and its jitter are
+//     hidden without a deeper shared-memory ring.
+// Linked slabs pull by default with this kernel (the neighbours' TMA producers read the boundary planes in place): its warps
+// advance in lock step, so a stalling peer store holds up the whole tile (fdtd_plan.cu, plan_prepare).
 // Arithmetic is the shared column4<EXACT>() => bit-identical to stencil_tb2_kernel and to two one-step launches
-// (tests/test_tb2_gpu.py runs every case through both kernels).
+// (tests/test_tb2_gpu.py runs every case through both kernels).  512^3 on one B200: 542-549 Gpts/s contracted (first kernel
+// 452-465), 410-416 bit-exact (245); DESIGN.md 4.5.
 #include "stencil_tb2.cuh"
 
 #include <type_traits>

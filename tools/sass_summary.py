@@ -10,7 +10,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 lib = os.path.join(ROOT, "accelerated-3d-acoustic-fdtd-kernel_b200", "libfdtd_b200.so")
 out = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True, check=True).stdout
-KEYS = ["UTMALDG", "SYNCS", "STG.E.128", "LDS.128", "LDS.64", "STS.128", "FFMA", "FADD", "FMUL", "MUFU.RCP", "LDG", "ATOM", "NANOSLEEP",
+KEYS = ["UTMALDG", "UTMAPF", "SYNCS", "STG.E.128", "LDS.128", "LDS.64", "STS.128", "FFMA", "FADD", "FMUL", "MUFU.RCP", "LDG", "ATOM", "NANOSLEEP",
         "ACQBULK", "ERRBAR", "MEMBAR", "CCTL"]
 arch = re.search(r"arch = (sm_\w+)", out)
 print(f"# {os.path.relpath(lib, ROOT)}: {arch.group(1) if arch else '?'}; instruction counts per kernel (static SASS, cuobjdump -sass)")
